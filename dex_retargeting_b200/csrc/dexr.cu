@@ -1,0 +1,584 @@
+// dexr.cu -- kernels' entry points and the C ABI of libdexr.so (see include/dexr.h).
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "dexr_kernels.cuh"
+
+namespace dexr {
+
+// ------------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------------
+struct FrameArgs {
+  const dexr_table_t* table;
+  dexr_params_t prm;
+  dexr_frames_t io;
+  long long B;
+  int T;          // frames per tile (multiple of 4)
+  int ntiles;
+  int use_bulk;   // inputs 16-byte aligned -> cp.async.bulk for full tiles
+  int in_row;     // floats per frame of the kp/ref input (63 or 3m)
+  int n_var, n_fixed, dof, len_proj;
+  int off_in, off_last, off_fixed, stage_bytes;  // ring stage layout (bytes)
+  int ring_off, bar_off, scratch_off;            // dynamic smem layout (bytes)
+};
+
+struct SeqArgs {
+  const dexr_table_t* table;
+  dexr_params_t prm;
+  dexr_sequences_t io;
+  long long S;
+  int steps;
+  int n_var, n_fixed, dof, len_proj;
+  int scratch_off;
+};
+
+// ------------------------------------------------------------------------------------------------
+// independent frames: producer warp (TMA ring) + NCW consumer warps
+// ------------------------------------------------------------------------------------------------
+template <int G, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const FrameArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTable* st = reinterpret_cast<SharedTable*>(smem);
+  unsigned char* ring = smem + a.ring_off;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
+  uint64_t* empty = full + 2;
+  int* next = reinterpret_cast<int*>(empty + 2);
+  float* scratch_base = reinterpret_cast<float*>(smem + a.scratch_off);
+
+  load_shared_table(*st, a.table);
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&empty[0], NCW);
+    mbar_init(&empty[1], NCW);
+    next[0] = 0;
+    next[1] = 0;
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool by_kp = a.io.keypoints != nullptr;
+  const float* g_in = by_kp ? a.io.keypoints : a.io.ref_value;
+
+  if (warp == NCW) {
+    // ===================== producer: stage tiles HBM -> shared memory =====================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int stage = it & 1;
+      if (it >= 2) mbar_wait(&empty[stage], ((it >> 1) - 1) & 1);
+      const long long f0 = (long long)tile * a.T;
+      const int count = (int)min((long long)a.T, a.B - f0);
+      unsigned char* sb = ring + stage * a.stage_bytes;
+      float* s_in = reinterpret_cast<float*>(sb + a.off_in);
+      float* s_last = reinterpret_cast<float*>(sb + a.off_last);
+      float* s_fixed = reinterpret_cast<float*>(sb + a.off_fixed);
+      const float* gi = g_in + f0 * a.in_row;
+      const float* gl = a.io.last_qpos + f0 * a.n_var;
+      const float* gf = a.n_fixed > 0 ? a.io.fixed_qpos + f0 * a.n_fixed : nullptr;
+      if (lane == 0) next[stage] = 0;
+      if (a.use_bulk && (count & 3) == 0) {
+        if (lane == 0) {
+          const uint32_t b_in = (uint32_t)count * a.in_row * 4u;
+          const uint32_t b_last = (uint32_t)count * a.n_var * 4u;
+          const uint32_t b_fixed = (uint32_t)count * a.n_fixed * 4u;
+          mbar_arrive_expect_tx(&full[stage], b_in + b_last + b_fixed);
+          bulk_g2s(s_in, gi, b_in, &full[stage]);
+          bulk_g2s(s_last, gl, b_last, &full[stage]);
+          if (b_fixed) bulk_g2s(s_fixed, gf, b_fixed, &full[stage]);
+        }
+      } else {
+        for (int i = lane; i < count * a.in_row; i += 32) s_in[i] = gi[i];
+        for (int i = lane; i < count * a.n_var; i += 32) s_last[i] = gl[i];
+        for (int i = lane; i < count * a.n_fixed; i += 32) s_fixed[i] = gf[i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ===================== consumers: one frame per group of G lanes =========================
+  constexpr int GPW = 32 / G;
+  const int gid = warp * GPW + (lane / G);
+  Solver<G> sv;
+  sv.init(a.table, st, scratch_base + (size_t)gid * Scratch<G>::kFloats, a.prm, lane);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    mbar_wait(&full[stage], (it >> 1) & 1);
+    const long long f0 = (long long)tile * a.T;
+    const int count = (int)min((long long)a.T, a.B - f0);
+    const unsigned char* sb = ring + stage * a.stage_bytes;
+    const float* s_in = reinterpret_cast<const float*>(sb + a.off_in);
+    const float* s_last = reinterpret_cast<const float*>(sb + a.off_last);
+    const float* s_fixed = reinterpret_cast<const float*>(sb + a.off_fixed);
+    while (true) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&next[stage], GPW);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= count) break;
+      const int idx = base + (lane / G);
+      const bool active = idx < count;
+      const int ci = active ? idx : base;
+      const long long f = f0 + ci;
+      FrameInputs in;
+      in.kp = by_kp ? s_in + ci * a.in_row : nullptr;
+      in.ref = by_kp ? nullptr : s_in + ci * a.in_row;
+      in.last = s_last + ci * a.n_var;
+      in.fixed = s_fixed + ci * a.n_fixed;
+      in.projected = a.io.projected ? a.io.projected + f * a.len_proj : nullptr;
+      const int status = sv.solve(in, active);
+      if (active) {
+        if (sv.var >= 0) a.io.qpos_out[f * a.n_var + sv.var] = sv.x;
+        if (a.io.robot_qpos_out && sv.l < a.dof) a.io.robot_qpos_out[f * a.dof + sv.l] = sv.q;
+        if (sv.l == 0) {
+          if (a.io.status_out) a.io.status_out[f] = status;
+          if (a.io.cost_out) a.io.cost_out[f] = sv.F;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequences: one group owns one stream and walks its T frames (seq_retarget.py:112-134)
+// ------------------------------------------------------------------------------------------------
+template <int G, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTable* st = reinterpret_cast<SharedTable*>(smem);
+  float* scratch_base = reinterpret_cast<float*>(smem + a.scratch_off);
+  load_shared_table(*st, a.table);
+  __syncthreads();
+
+  constexpr int GPW = 32 / G;
+  constexpr int KPL = (3 * DEXR_NUM_KEYPOINTS + G - 1) / G;  // keypoint floats per lane
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int gid = warp * GPW + (lane / G);
+  const int groups_per_cta = NW * GPW;
+  float* scratch = scratch_base + (size_t)gid * (Scratch<G>::kFloats + 64);
+  float* kpbuf = scratch + Scratch<G>::kFloats;  // 63 floats, this group's current keypoints
+  Solver<G> sv;
+  sv.init(a.table, st, scratch, a.prm, lane);
+  const int l = sv.l;
+  const bool use_filter = a.prm.lp_alpha >= 0.f && a.prm.lp_alpha <= 1.f;
+
+  for (long long s0 = (long long)blockIdx.x * groups_per_cta; s0 < a.S; s0 += (long long)gridDim.x * groups_per_cta) {
+    // all groups of a warp must walk the time loop together (warp-wide shuffles inside solve)
+    const long long s = s0 + gid;
+    const bool active = s < a.S;
+    const long long sc = active ? s : a.S - 1;
+    float last = 0.f, fy = 0.f;
+    int finit = 0;
+    if (active && sv.var >= 0) last = a.io.last_qpos[sc * a.n_var + sv.var];
+    if (active && use_filter && l < a.dof) fy = a.io.filter_state[sc * a.dof + l];
+    if (active && use_filter) finit = a.io.filter_init[sc];
+    const float* kp_stream = a.io.keypoints + sc * a.steps * (3 * DEXR_NUM_KEYPOINTS);
+    float pre[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int e = l + j * G;
+      pre[j] = (e < 3 * DEXR_NUM_KEYPOINTS) ? kp_stream[e] : 0.f;
+    }
+    for (int t = 0; t < a.steps; ++t) {
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const int e = l + j * G;
+        if (e < 3 * DEXR_NUM_KEYPOINTS) kpbuf[e] = pre[j];
+      }
+      if (t + 1 < a.steps) {
+        const float* nxt = kp_stream + (long long)(t + 1) * (3 * DEXR_NUM_KEYPOINTS);
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const int e = l + j * G;
+          pre[j] = (e < 3 * DEXR_NUM_KEYPOINTS) ? nxt[e] : 0.f;
+        }
+      }
+      // stash the warm start where solve() reads it: reuse the tail of kpbuf (floats 63 is pad) -> use at()
+      __syncwarp();
+      FrameInputs in;
+      in.kp = kpbuf;
+      in.ref = nullptr;
+      in.fixed = a.n_fixed > 0 ? a.io.fixed_qpos + (sc * a.steps + t) * a.n_fixed : nullptr;
+      in.last = nullptr;  // warm start comes from the register `x` (previous solution)
+      in.projected = a.io.projected ? a.io.projected + sc * a.len_proj : nullptr;
+      sv.x = last;
+      const int status = sv.solve(in, active);
+      last = sv.x;  // unfiltered solution is the next warm start (seq_retarget.py:124)
+      float out = sv.q;
+      if (use_filter) {  // optimizer_utils.py:7-13
+        fy = finit ? fmaf(a.prm.lp_alpha, out - fy, fy) : out;
+        finit = 1;
+        out = fy;
+      }
+      if (active) {
+        if (l < a.dof) a.io.robot_qpos_out[(sc * a.steps + t) * a.dof + l] = out;
+        if (l == 0 && a.io.status_out) a.io.status_out[sc * a.steps + t] = status;
+      }
+      __syncwarp();
+    }
+    if (active) {
+      if (sv.var >= 0) a.io.last_qpos[sc * a.n_var + sv.var] = last;
+      if (use_filter && l < a.dof) a.io.filter_state[sc * a.dof + l] = fy;
+      if (use_filter && l == 0) a.io.filter_init[sc] = (uint8_t)finit;
+    }
+  }
+}
+
+}  // namespace dexr
+
+// ================================================================================================
+// host side: handle, launches, C ABI
+// ================================================================================================
+using namespace dexr;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(DEXR_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct dexr_robot {
+  int device = 0;
+  int num_sms = 0;
+  dexr_table_t* table_dev = nullptr;
+  dexr_table_t host;  // header + small arrays used for validation / sizing
+  dexr_launch_info_t last{};
+  // staging for dexr_solve_frames_host
+  std::mutex mu;
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  void* stage_dev[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+};
+
+constexpr int kFramesNCW = 11;  // consumer warps per CTA (frames kernel)
+constexpr int kSeqNW = 8;       // warps per CTA (sequences kernel)
+constexpr int kMaxTile = 64;
+
+static int validate_table(const dexr_table_t* t) {
+  if (t->magic != 0x31525844u) return fail(DEXR_E_INVALID, "robot table: bad magic 0x%08x", t->magic);
+  if (t->nbytes != sizeof(dexr_table_t))
+    return fail(DEXR_E_INVALID, "robot table: size %u does not match library (%zu)", t->nbytes, sizeof(dexr_table_t));
+  if (t->dof < 1 || t->dof > DEXR_MAX_LANES) return fail(DEXR_E_INVALID, "robot table: dof %d out of range 1..32", t->dof);
+  if (t->n_var < 1 || t->n_var > t->dof) return fail(DEXR_E_INVALID, "robot table: n_var %d out of range", t->n_var);
+  if (t->n_fixed < 0 || t->n_fixed > t->dof) return fail(DEXR_E_INVALID, "robot table: n_fixed %d out of range", t->n_fixed);
+  if (t->n_links < 1 || t->n_links > DEXR_MAX_LINKS) return fail(DEXR_E_INVALID, "robot table: n_links %d out of range", t->n_links);
+  if (t->n_res < 1 || t->n_res > DEXR_MAX_RES) return fail(DEXR_E_INVALID, "robot table: n_res %d out of range", t->n_res);
+  if (t->loss < 0 || t->loss > 2) return fail(DEXR_E_INVALID, "robot table: loss %d unknown", t->loss);
+  if (t->n_rounds < 0 || t->n_rounds > 5) return fail(DEXR_E_INVALID, "robot table: n_rounds %d out of range", t->n_rounds);
+  if (t->loss == DEXR_LOSS_DEXPILOT && (t->len_proj < 1 || t->len_proj > t->n_res || t->len_s1 > t->len_proj))
+    return fail(DEXR_E_INVALID, "robot table: dexpilot projection sizes inconsistent");
+  for (int k = 0; k < t->n_res; ++k) {
+    if (t->res_task[k] < 0 || t->res_task[k] >= t->n_links || t->res_origin[k] >= t->n_links)
+      return fail(DEXR_E_INVALID, "robot table: residual %d refers to an unknown link", k);
+    if (t->res_human_task[k] < 0 || t->res_human_task[k] >= DEXR_NUM_KEYPOINTS ||
+        t->res_human_origin[k] >= DEXR_NUM_KEYPOINTS)
+      return fail(DEXR_E_INVALID, "robot table: residual %d human index out of range", k);
+  }
+  for (int k = 0; k < t->n_links; ++k)
+    if (t->link_parent[k] >= t->dof) return fail(DEXR_E_INVALID, "robot table: link %d parent out of range", k);
+  return 0;
+}
+
+static int finish_create(dexr_robot* r, dexr_robot_t** out) {
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, r->device));
+  if (prop.major < 10) {
+    delete r;
+    return fail(DEXR_E_NODEVICE, "device %d is sm_%d%d; libdexr is built for sm_100a only", r->device, prop.major, prop.minor);
+  }
+  r->num_sms = prop.multiProcessorCount;
+  *out = r;
+  return 0;
+}
+
+extern "C" {
+
+int dexr_version(void) { return DEXR_VERSION; }
+const char* dexr_last_error(void) { return g_err; }
+size_t dexr_table_sizeof(void) { return sizeof(dexr_table_t); }
+size_t dexr_params_sizeof(void) { return sizeof(dexr_params_t); }
+
+void dexr_default_params(dexr_params_t* p) {
+  p->huber_delta = 0.02f;
+  p->norm_delta = 4e-3f;
+  p->scaling = 1.0f;
+  p->project_dist = 0.03f;
+  p->escape_dist = 0.05f;
+  p->eta1 = 1e-4f;
+  p->eta2 = 3e-2f;
+  p->lp_alpha = -1.0f;
+  p->tol = 1e-5f;
+  p->lambda0 = 1e-3f;
+  p->max_iters = 64;
+  p->clip_init = 0;
+}
+
+int dexr_robot_create(const dexr_table_t* table_host, int device, dexr_robot_t** out) {
+  if (!table_host || !out) return fail(DEXR_E_INVALID, "dexr_robot_create: null argument");
+  if (int e = validate_table(table_host)) return e;
+  CUDA_TRY(cudaSetDevice(device));
+  dexr_robot* r = new (std::nothrow) dexr_robot();
+  if (!r) return fail(DEXR_E_INVALID, "out of host memory");
+  r->device = device;
+  r->host = *table_host;
+  CUDA_TRY(cudaMalloc(&r->table_dev, sizeof(dexr_table_t)));
+  CUDA_TRY(cudaMemcpy(r->table_dev, table_host, sizeof(dexr_table_t), cudaMemcpyHostToDevice));
+  return finish_create(r, out);
+}
+
+int dexr_robot_create_from_device(const void* table_dev, size_t nbytes, int device, dexr_robot_t** out) {
+  if (!table_dev || !out) return fail(DEXR_E_INVALID, "dexr_robot_create_from_device: null argument");
+  if (nbytes != sizeof(dexr_table_t)) return fail(DEXR_E_INVALID, "table size %zu != %zu", nbytes, sizeof(dexr_table_t));
+  CUDA_TRY(cudaSetDevice(device));
+  dexr_robot* r = new (std::nothrow) dexr_robot();
+  if (!r) return fail(DEXR_E_INVALID, "out of host memory");
+  r->device = device;
+  CUDA_TRY(cudaMalloc(&r->table_dev, sizeof(dexr_table_t)));
+  CUDA_TRY(cudaMemcpy(r->table_dev, table_dev, sizeof(dexr_table_t), cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(&r->host, r->table_dev, sizeof(dexr_table_t), cudaMemcpyDeviceToHost));
+  if (int e = validate_table(&r->host)) {
+    cudaFree(r->table_dev);
+    delete r;
+    return e;
+  }
+  return finish_create(r, out);
+}
+
+const void* dexr_robot_device_table(const dexr_robot_t* robot) { return robot ? robot->table_dev : nullptr; }
+
+void dexr_robot_destroy(dexr_robot_t* robot) {
+  if (!robot) return;
+  cudaSetDevice(robot->device);
+  for (int i = 0; i < 2; ++i) {
+    if (robot->streams[i]) cudaStreamDestroy(robot->streams[i]);
+    if (robot->stage_dev[i]) cudaFree(robot->stage_dev[i]);
+  }
+  if (robot->table_dev) cudaFree(robot->table_dev);
+  delete robot;
+}
+
+}  // extern "C"
+
+static int check_params(const dexr_params_t* p) {
+  if (!(p->huber_delta > 0.f)) return fail(DEXR_E_INVALID, "huber_delta must be > 0");
+  if (!(p->norm_delta >= 0.f)) return fail(DEXR_E_INVALID, "norm_delta must be >= 0");
+  if (p->max_iters < 1 || p->max_iters > 65535) return fail(DEXR_E_INVALID, "max_iters out of range");
+  if (!(p->tol > 0.f) || !(p->lambda0 > 0.f)) return fail(DEXR_E_INVALID, "tol and lambda0 must be > 0");
+  return 0;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <int G>
+static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+  const dexr_table_t& t = r->host;
+  FrameArgs a{};
+  a.table = r->table_dev;
+  a.prm = *prm;
+  a.io = *io;
+  a.B = B;
+  a.n_var = t.n_var; a.n_fixed = t.n_fixed; a.dof = t.dof; a.len_proj = t.len_proj;
+  a.in_row = io->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
+  const int slots = r->num_sms;  // one CTA per SM
+  long long per = (B + slots - 1) / slots;
+  int T = (int)std::min<long long>(kMaxTile, std::max<long long>(4, per));
+  T = round_up(T, 4);
+  a.T = T;
+  a.ntiles = (int)((B + T - 1) / T);
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  a.use_bulk = aligned16(io->keypoints ? io->keypoints : io->ref_value) && aligned16(io->last_qpos) &&
+               (t.n_fixed == 0 || aligned16(io->fixed_qpos));
+  a.off_in = 0;
+  a.off_last = round_up(T * a.in_row * 4, 16);
+  a.off_fixed = a.off_last + round_up(T * t.n_var * 4, 16);
+  a.stage_bytes = a.off_fixed + round_up(T * std::max(t.n_fixed, 1) * 4, 16);
+  a.ring_off = round_up((int)sizeof(SharedTable), 16);
+  a.bar_off = a.ring_off + 2 * a.stage_bytes;
+  a.scratch_off = round_up(a.bar_off + 4 * 8 + 2 * 4, 16);
+  constexpr int GPW = 32 / G;
+  const int smem = a.scratch_off + kFramesNCW * GPW * Scratch<G>::kFloats * 4;
+  auto kern = dexr_frames_kernel<G, kFramesNCW>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = std::min(a.ntiles, slots);
+  kern<<<grid, (kFramesNCW + 1) * 32, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  r->last = dexr_launch_info_t{grid, (kFramesNCW + 1) * 32, smem, T, G, kFramesNCW, r->last.kernels_launched + 1};
+  return 0;
+}
+
+extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t* params, const dexr_frames_t* io,
+                                 int64_t num_frames, void* cuda_stream) {
+  if (!robot || !params || !io) return fail(DEXR_E_INVALID, "dexr_solve_frames: null argument");
+  if (num_frames < 0) return fail(DEXR_E_INVALID, "num_frames < 0");
+  if (num_frames == 0) return 0;
+  if (int e = check_params(params)) return e;
+  const dexr_table_t& t = robot->host;
+  if ((io->keypoints != nullptr) == (io->ref_value != nullptr))
+    return fail(DEXR_E_INVALID, "exactly one of keypoints / ref_value must be given");
+  if (!io->last_qpos || !io->qpos_out) return fail(DEXR_E_INVALID, "last_qpos and qpos_out are required");
+  if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
+  CUDA_TRY(cudaSetDevice(robot->device));
+  dexr_robot* r = const_cast<dexr_robot*>(robot);
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  return t.dof <= 16 ? launch_frames<16>(r, params, io, num_frames, stream)
+                     : launch_frames<32>(r, params, io, num_frames, stream);
+}
+
+template <int G>
+static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_sequences_t* io, long long S, int steps,
+                            cudaStream_t stream) {
+  const dexr_table_t& t = r->host;
+  SeqArgs a{};
+  a.table = r->table_dev;
+  a.prm = *prm;
+  a.prm.clip_init = 1;  // SeqRetargeting.retarget always clips the warm start (seq_retarget.py:118-120)
+  a.io = *io;
+  a.S = S;
+  a.steps = steps;
+  a.n_var = t.n_var; a.n_fixed = t.n_fixed; a.dof = t.dof; a.len_proj = t.len_proj;
+  a.scratch_off = round_up((int)sizeof(SharedTable), 16);
+  constexpr int GPW = 32 / G;
+  const int groups = kSeqNW * GPW;
+  const int smem = a.scratch_off + groups * (Scratch<G>::kFloats + 64) * 4;
+  auto kern = dexr_sequences_kernel<G, kSeqNW>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // spread streams over as many SMs as possible: latency bound, one stream per group
+  long long ctas = (S + groups - 1) / groups;
+  int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * 2);
+  if (S < (long long)r->num_sms * groups) grid = (int)std::min<long long>(r->num_sms, std::max<long long>(1, S));
+  kern<<<grid, kSeqNW * 32, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  r->last = dexr_launch_info_t{grid, kSeqNW * 32, smem, 0, G, kSeqNW, r->last.kernels_launched + 1};
+  return 0;
+}
+
+extern "C" int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params_t* params, const dexr_sequences_t* io,
+                                    int64_t num_streams, int64_t num_steps, void* cuda_stream) {
+  if (!robot || !params || !io) return fail(DEXR_E_INVALID, "dexr_solve_sequences: null argument");
+  if (num_streams < 0 || num_steps < 0 || num_steps > INT32_MAX) return fail(DEXR_E_INVALID, "bad sizes");
+  if (num_streams == 0 || num_steps == 0) return 0;
+  if (int e = check_params(params)) return e;
+  const dexr_table_t& t = robot->host;
+  if (!io->keypoints || !io->last_qpos || !io->robot_qpos_out) return fail(DEXR_E_INVALID, "keypoints, last_qpos, robot_qpos_out required");
+  const bool use_filter = params->lp_alpha >= 0.f && params->lp_alpha <= 1.f;
+  if (use_filter && (!io->filter_state || !io->filter_init)) return fail(DEXR_E_INVALID, "low-pass filter needs filter_state and filter_init");
+  if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
+  CUDA_TRY(cudaSetDevice(robot->device));
+  dexr_robot* r = const_cast<dexr_robot*>(robot);
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  return t.dof <= 16 ? launch_sequences<16>(r, params, io, num_streams, (int)num_steps, stream)
+                     : launch_sequences<32>(r, params, io, num_streams, (int)num_steps, stream);
+}
+
+extern "C" {
+
+int dexr_get_launch_info(const dexr_robot_t* robot, dexr_launch_info_t* out) {
+  if (!robot || !out) return fail(DEXR_E_INVALID, "null argument");
+  *out = robot->last;
+  return 0;
+}
+
+// Host-buffer entry: chunked, two internal streams so that chunk i+1's H2D overlaps chunk i's solve
+// and chunk i-1's D2H.  Pointers in `io_host` are host pointers (pinned for true overlap).
+int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, const dexr_frames_t* h, int64_t B) {
+  if (!robot || !params || !h) return fail(DEXR_E_INVALID, "dexr_solve_frames_host: null argument");
+  if (B < 0) return fail(DEXR_E_INVALID, "num_frames < 0");
+  if (B == 0) return 0;
+  if ((h->keypoints != nullptr) == (h->ref_value != nullptr))
+    return fail(DEXR_E_INVALID, "exactly one of keypoints / ref_value must be given");
+  if (!h->last_qpos || !h->qpos_out) return fail(DEXR_E_INVALID, "last_qpos and qpos_out are required");
+  std::lock_guard<std::mutex> lock(robot->mu);
+  const dexr_table_t& t = robot->host;
+  if (t.n_fixed > 0 && !h->fixed_qpos) return fail(DEXR_E_INVALID, "fixed_qpos is NULL");
+  CUDA_TRY(cudaSetDevice(robot->device));
+  const int in_row = h->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
+  // per-frame device bytes, every sub-array padded so that chunk bases stay 16-byte aligned
+  const size_t row_in = in_row * 4, row_last = t.n_var * 4, row_fixed = t.n_fixed * 4, row_proj = t.len_proj,
+               row_q = t.n_var * 4, row_rq = h->robot_qpos_out ? t.dof * 4 : 0, row_st = h->status_out ? 4 : 0,
+               row_c = h->cost_out ? 4 : 0;
+  const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, round_up((int)std::min<int64_t>((B + 3) / 4, 1 << 20), 64)));
+  auto pad = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t need = pad(chunk * row_in) + pad(chunk * row_last) + pad(chunk * row_fixed) + pad(chunk * row_proj) +
+                      pad(chunk * row_q) + pad(chunk * row_rq) + pad(chunk * row_st) + pad(chunk * row_c);
+  for (int i = 0; i < 2; ++i) {
+    if (!robot->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&robot->streams[i], cudaStreamNonBlocking));
+    if (robot->stage_bytes < need) {
+      if (robot->stage_dev[i]) CUDA_TRY(cudaFree(robot->stage_dev[i]));
+      robot->stage_dev[i] = nullptr;
+      CUDA_TRY(cudaMalloc(&robot->stage_dev[i], need));
+    }
+  }
+  robot->stage_bytes = std::max(robot->stage_bytes, need);
+  int ci = 0;
+  for (int64_t f0 = 0; f0 < B; f0 += chunk, ci ^= 1) {
+    const int64_t n = std::min<int64_t>(chunk, B - f0);
+    cudaStream_t s = robot->streams[ci];
+    unsigned char* base = static_cast<unsigned char*>(robot->stage_dev[ci]);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { unsigned char* p = base + off; off += pad(bytes); return p; };
+    float* d_in = reinterpret_cast<float*>(take(chunk * row_in));
+    float* d_last = reinterpret_cast<float*>(take(chunk * row_last));
+    float* d_fixed = reinterpret_cast<float*>(take(chunk * row_fixed));
+    uint8_t* d_proj = reinterpret_cast<uint8_t*>(take(chunk * row_proj));
+    float* d_q = reinterpret_cast<float*>(take(chunk * row_q));
+    float* d_rq = reinterpret_cast<float*>(take(chunk * row_rq));
+    int32_t* d_st = reinterpret_cast<int32_t*>(take(chunk * row_st));
+    float* d_c = reinterpret_cast<float*>(take(chunk * row_c));
+    const float* h_in = h->keypoints ? h->keypoints : h->ref_value;
+    CUDA_TRY(cudaMemcpyAsync(d_in, h_in + f0 * in_row, n * row_in, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_last, h->last_qpos + f0 * t.n_var, n * row_last, cudaMemcpyHostToDevice, s));
+    if (t.n_fixed) CUDA_TRY(cudaMemcpyAsync(d_fixed, h->fixed_qpos + f0 * t.n_fixed, n * row_fixed, cudaMemcpyHostToDevice, s));
+    const bool proj = h->projected && t.len_proj > 0;
+    if (proj) CUDA_TRY(cudaMemcpyAsync(d_proj, h->projected + f0 * t.len_proj, n * row_proj, cudaMemcpyHostToDevice, s));
+    dexr_frames_t d{};
+    d.keypoints = h->keypoints ? d_in : nullptr;
+    d.ref_value = h->keypoints ? nullptr : d_in;
+    d.last_qpos = d_last;
+    d.fixed_qpos = t.n_fixed ? d_fixed : nullptr;
+    d.projected = proj ? d_proj : nullptr;
+    d.qpos_out = d_q;
+    d.robot_qpos_out = h->robot_qpos_out ? d_rq : nullptr;
+    d.status_out = h->status_out ? d_st : nullptr;
+    d.cost_out = h->cost_out ? d_c : nullptr;
+    if (int e = dexr_solve_frames(robot, params, &d, n, s)) return e;
+    CUDA_TRY(cudaMemcpyAsync(h->qpos_out + f0 * t.n_var, d_q, n * row_q, cudaMemcpyDeviceToHost, s));
+    if (h->robot_qpos_out) CUDA_TRY(cudaMemcpyAsync(h->robot_qpos_out + f0 * t.dof, d_rq, n * row_rq, cudaMemcpyDeviceToHost, s));
+    if (h->status_out) CUDA_TRY(cudaMemcpyAsync(h->status_out + f0, d_st, n * row_st, cudaMemcpyDeviceToHost, s));
+    if (h->cost_out) CUDA_TRY(cudaMemcpyAsync(h->cost_out + f0, d_c, n * row_c, cudaMemcpyDeviceToHost, s));
+    if (proj) CUDA_TRY(cudaMemcpyAsync(h->projected + f0 * t.len_proj, d_proj, n * row_proj, cudaMemcpyDeviceToHost, s));
+    // the staging buffer of this stream is reused two chunks later: same stream => ordered
+  }
+  CUDA_TRY(cudaStreamSynchronize(robot->streams[0]));
+  CUDA_TRY(cudaStreamSynchronize(robot->streams[1]));
+  return 0;
+}
+
+}  // extern "C"

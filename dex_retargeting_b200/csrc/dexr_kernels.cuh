@@ -1,0 +1,674 @@
+// dexr_kernels.cuh -- the fused per-frame retargeting solver for sm_100a.
+//
+// One group of G lanes (G = 16 or 32, so one or two hand-frames per warp) owns one hand-frame.
+// Lane c of the group is movable joint c of the robot in pinocchio DoF order.  Everything the
+// reference does per frame on the CPU through nlopt + pinocchio + torch
+// (optimizer.py:77-102, 146-198, 249-304, 510-575; robot_wrapper.py:82-95;
+// kinematics_adaptor.py:102-113 -- paths relative to /root/reference/src/dex_retargeting) happens here
+// without leaving the SM:
+//   * forward kinematics by pointer jumping over the joint tree (log2(depth) rounds of a 12-float
+//     warp shuffle + 3x4 compose), joint constants resident in registers for the kernel's lifetime;
+//   * world-aligned linear Jacobian columns a_c x (p_link - p_c), one column per lane;
+//   * the Position / Vector / DexPilot Huber objective, its exact gradient and its exact Hessian:
+//     sum_k Jv_k^T (d2 loss/dr2) Jv_k  +  FK curvature  a_i . sum_l (J_lj x dF/dp_l)  +  2 norm_delta I,
+//     built by broadcasting Jacobian rows through shared memory;
+//   * a bounded Levenberg-Marquardt / Newton iteration: active-set freeze at the box bounds,
+//     in-register Cholesky (lane = row) with fused forward substitution, shared-memory-transposed
+//     back substitution, noise-aware step acceptance in fp32;
+//   * DexPilot hysteresis flags, weights and projected targets (optimizer.py:456-508);
+//   * for sequences, SeqRetargeting's clip -> solve -> scatter -> mimic -> low-pass recurrence
+//     (seq_retarget.py:112-134, optimizer_utils.py:7-13) carried in registers across time steps.
+// Inputs of a batch are staged HBM -> shared memory by a producer warp with cp.async.bulk (TMA 1-D)
+// into a two-stage ring guarded by mbarriers; consumer groups claim frames from the ring dynamically.
+// No tensor cores: n <= 32 unknowns per frame, the work is FP32 issue / latency bound.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dexr.h"
+
+namespace dexr {
+
+constexpr int kMaxTrials = 8;
+constexpr float kNoise = 2e-6f;      // relative fp32 noise floor of the objective value
+constexpr float kLamMin = 1e-7f;
+constexpr float kLamDown = 0.1f;
+constexpr float kLamUp = 10.0f;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ float gshfl(float v, int src) {
+  return __shfl_sync(0xffffffffu, v, src, G);
+}
+template <int G>
+__device__ __forceinline__ int gshfl_i(int v, int src) {
+  return __shfl_sync(0xffffffffu, v, src, G);
+}
+template <int G>
+__device__ __forceinline__ float gsum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float gmax(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, G));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ bool gany(bool p, int lane) {
+  unsigned b = __ballot_sync(0xffffffffu, p);
+  if (G == 32) return b != 0u;
+  return ((b >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u)) != 0u;
+}
+template <int G>
+__device__ __forceinline__ unsigned gballot(bool p, int lane) {
+  unsigned b = __ballot_sync(0xffffffffu, p);
+  if (G == 32) return b;
+  return (b >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u);
+}
+
+__device__ __forceinline__ float huber_val(float d, float beta, float inv_beta) {
+  return d < beta ? 0.5f * d * d * inv_beta : d - 0.5f * beta;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// uniform (per CTA) slice of the robot table kept in shared memory
+// ------------------------------------------------------------------------------------------------
+struct SharedTable {
+  float4 link_off[DEXR_MAX_LINKS];  // xyz, w = parent lane as int bits
+  uint32_t link_anc[DEXR_MAX_LINKS];
+  int res_task[DEXR_MAX_RES], res_origin[DEXR_MAX_RES], res_ht[DEXR_MAX_RES], res_ho[DEXR_MAX_RES];
+  int s2_origin[DEXR_MAX_RES], s2_task[DEXR_MAX_RES];
+  int group_count[DEXR_MAX_LANES];
+  int group_lane[DEXR_MAX_LANES][DEXR_MAX_GROUP];
+  float group_mult[DEXR_MAX_LANES][DEXR_MAX_GROUP];
+  int dof, n_var, n_fixed, n_links, n_res, loss, n_rounds, has_mimic, num_fingers, len_proj, len_s1;
+};
+
+__device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __restrict__ tb) {
+  for (int i = threadIdx.x; i < DEXR_MAX_LINKS; i += blockDim.x) {
+    st.link_off[i] = make_float4(tb->link_off[i][0], tb->link_off[i][1], tb->link_off[i][2],
+                                 __int_as_float(tb->link_parent[i]));
+    st.link_anc[i] = tb->link_anc_mask[i];
+  }
+  for (int i = threadIdx.x; i < DEXR_MAX_RES; i += blockDim.x) {
+    st.res_task[i] = tb->res_task[i];
+    st.res_origin[i] = tb->res_origin[i];
+    st.res_ht[i] = tb->res_human_task[i];
+    st.res_ho[i] = tb->res_human_origin[i];
+    st.s2_origin[i] = tb->s2_origin[i];
+    st.s2_task[i] = tb->s2_task[i];
+  }
+  for (int i = threadIdx.x; i < DEXR_MAX_LANES; i += blockDim.x) {
+    st.group_count[i] = tb->group_count[i];
+    for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
+      st.group_lane[i][f] = tb->group_lane[i][f];
+      st.group_mult[i][f] = tb->group_mult[i][f];
+    }
+  }
+  if (threadIdx.x == 0) {
+    st.dof = tb->dof; st.n_var = tb->n_var; st.n_fixed = tb->n_fixed; st.n_links = tb->n_links;
+    st.n_res = tb->n_res; st.loss = tb->loss; st.n_rounds = tb->n_rounds; st.has_mimic = tb->has_mimic;
+    st.num_fingers = tb->num_fingers; st.len_proj = tb->len_proj; st.len_s1 = tb->len_s1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-group scratch in shared memory (floats)
+// ------------------------------------------------------------------------------------------------
+template <int G>
+struct Scratch {
+  static constexpr int NP = G;
+  static constexpr int kFr = 0;                                 // [MAX_RES][4] target xyz, weight c_k
+  static constexpr int kLp = kFr + DEXR_MAX_RES * 4;            // [2][MAX_LINKS][4] link positions
+  static constexpr int kU = kLp + 2 * DEXR_MAX_LINKS * 4;       // union: jbuf[2][3][NP] + at[NP][8]  |  Lrow[NP][NP]
+  static constexpr int kUSize = (NP * NP > 14 * NP) ? NP * NP : 14 * NP;
+  static constexpr int kHb = kU + kUSize;                       // [NP][NP]   Hessian backup, column per lane
+  static constexpr int kLcol = kHb + NP * NP;                   // [NP][NP+1] L^T rows, conflict-free column reads
+  static constexpr int kFloats = ((kLcol + NP * (NP + 1) + 3) / 4) * 4;
+};
+
+// ------------------------------------------------------------------------------------------------
+// the solver: lane constants + per-frame state in registers
+// ------------------------------------------------------------------------------------------------
+struct FrameInputs {
+  const float* kp;     // 63 floats (keypoints mode) or nullptr
+  const float* ref;    // m*3 floats (ref mode) or nullptr
+  const float* fixed;  // n_fixed floats or nullptr
+  const float* last;   // n_var floats
+  uint8_t* projected;  // len_proj flags (global) or nullptr
+};
+
+template <int G>
+struct Solver {
+  static constexpr int NP = G;
+  using SC = Scratch<G>;
+
+  // ---- lane constants (whole kernel) ----
+  float R0[9], RA[9], RB[9], p0[3], d0[3], ax[3];
+  float lo, hi, clo, chi, mmult, moff;
+  int jtype, var, fixedi, msrc;
+  uint32_t jump, anc, desc;
+  int gcount, glane[DEXR_MAX_GROUP];
+  float gmult[DEXR_MAX_GROUP];
+  int l;     // lane within group
+  int lane;  // lane within warp
+  const SharedTable* st;
+  float* sc;  // group scratch
+  dexr_params_t prm;
+  float inv_beta;
+
+  // ---- per-frame state ----
+  float x, x0, q, qfix;       // variable value, anchor, full joint value, fixed value
+  float R[9], p[3], a[3];     // world placement of this joint frame, world axis (at accepted x)
+  float F;                    // objective at x
+  int cur;                    // which link-position buffer holds the accepted positions
+
+  __device__ void init(const dexr_table_t* __restrict__ tb, const SharedTable* st_, float* scratch,
+                       const dexr_params_t& prm_, int lane_) {
+    st = st_; sc = scratch; prm = prm_; lane = lane_; l = lane_ & (G - 1);
+    inv_beta = 1.0f / prm.huber_delta;
+    const int c = l < DEXR_MAX_LANES ? l : 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { R0[i] = tb->R0[c][i]; RA[i] = tb->RA[c][i]; RB[i] = tb->RB[c][i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p0[i] = tb->p0[c][i]; d0[i] = tb->d0[c][i]; ax[i] = tb->axis[c][i]; }
+    lo = tb->lower[c]; hi = tb->upper[c]; clo = tb->clip_lo[c]; chi = tb->clip_hi[c];
+    mmult = tb->mimic_mult[c]; moff = tb->mimic_off[c];
+    jtype = tb->jtype[c]; var = tb->var_index[c]; fixedi = tb->fixed_index[c]; msrc = tb->mimic_src[c];
+    jump = tb->jump[c]; anc = tb->anc_mask[c]; desc = tb->desc_mask[c];
+    gcount = tb->group_count[c];
+#pragma unroll
+    for (int f = 0; f < DEXR_MAX_GROUP; ++f) { glane[f] = tb->group_lane[c][f]; gmult[f] = tb->group_mult[c][f]; }
+  }
+
+  __device__ __forceinline__ float4* fr() const { return reinterpret_cast<float4*>(sc + SC::kFr); }
+  __device__ __forceinline__ float4* lp(int b) const { return reinterpret_cast<float4*>(sc + SC::kLp) + b * DEXR_MAX_LINKS; }
+  __device__ __forceinline__ float* jbuf(int b, int comp) const { return sc + SC::kU + (b * 3 + comp) * NP; }
+  __device__ __forceinline__ float4* at() const { return reinterpret_cast<float4*>(sc + SC::kU + 6 * NP); }
+  __device__ __forceinline__ float* lrow() const { return sc + SC::kU; }
+  __device__ __forceinline__ float* hb() const { return sc + SC::kHb; }
+  __device__ __forceinline__ float* lcol() const { return sc + SC::kLcol; }
+
+  // q of every joint from the variables: target joints copy, fixed joints constant, mimic affine.
+  // (optimizer.py:147-151 + kinematics_adaptor.py:102-105)
+  __device__ __forceinline__ float compose_q(float xv) const {
+    const float src = gshfl<G>(xv, msrc >= 0 ? msrc : l);
+    return var >= 0 ? xv : (msrc >= 0 ? fmaf(mmult, src, moff) : qfix);
+  }
+
+  // Forward kinematics (robot_wrapper.py:82-83 [pinocchio forwardKinematics]) by pointer jumping.
+  __device__ __forceinline__ void fk(float qv, float* Ro, float* po) const {
+    float s, c;
+    sincosf(qv, &s, &c);
+    const float omc = 1.0f - c;
+    if (jtype == 0) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Ro[i] = fmaf(s, RA[i], fmaf(omc, RB[i], R0[i]));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) po[i] = p0[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Ro[i] = R0[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) po[i] = fmaf(qv, d0[i], p0[i]);
+    }
+    const int rounds = st->n_rounds;
+    for (int r = 0; r < rounds; ++r) {
+      const int src = (jump >> (6 * r)) & 63;
+      const bool has = src != 63;
+      const int sl = has ? src : l;
+      float Rs[9], ps[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rs[i] = gshfl<G>(Ro[i], sl);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ps[i] = gshfl<G>(po[i], sl);
+      if (has) {
+        float Rn[9], pn[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            Rn[3 * i + j] = fmaf(Rs[3 * i], Ro[j], fmaf(Rs[3 * i + 1], Ro[3 + j], Rs[3 * i + 2] * Ro[6 + j]));
+          pn[i] = fmaf(Rs[3 * i], po[0], fmaf(Rs[3 * i + 1], po[1], fmaf(Rs[3 * i + 2], po[2], ps[i])));
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ro[i] = Rn[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) po[i] = pn[i];
+      }
+    }
+  }
+
+  // Link origins (robot_wrapper.py:85-87 [updateFramePlacement]) -> shared buffer b.
+  __device__ __forceinline__ void write_links(const float* Rw, const float* pw, int b) const {
+    float4* out = lp(b);
+    const int L = st->n_links;
+    for (int k = 0; k < L; ++k) {
+      const float4 o = st->link_off[k];
+      const int par = __float_as_int(o.w);
+      if (par == l) {
+        out[k] = make_float4(fmaf(Rw[0], o.x, fmaf(Rw[1], o.y, fmaf(Rw[2], o.z, pw[0]))),
+                             fmaf(Rw[3], o.x, fmaf(Rw[4], o.y, fmaf(Rw[5], o.z, pw[1]))),
+                             fmaf(Rw[6], o.x, fmaf(Rw[7], o.y, fmaf(Rw[8], o.z, pw[2]))), 0.f);
+      } else if (par < 0 && l == 0) {
+        out[k] = make_float4(o.x, o.y, o.z, 0.f);
+      }
+    }
+  }
+
+  // Objective L(x) + norm_delta |x - x0|^2 from link buffer b (value part of optimizer.py:162-167,
+  // 263-274, 524-541, with the regulariser the reference only puts into the gradient).
+  __device__ __forceinline__ float cost(int b, float xv) const {
+    float v = 0.f;
+    const int m = st->n_res;
+    if (l < m) {
+      const float4 T = fr()[l];
+      const int ti = st->res_task[l], oi = st->res_origin[l];
+      const float4 pt = lp(b)[ti];
+      float rx = pt.x - T.x, ry = pt.y - T.y, rz = pt.z - T.z;
+      if (oi >= 0) {
+        const float4 po = lp(b)[oi];
+        rx -= po.x; ry -= po.y; rz -= po.z;
+      }
+      const float beta = prm.huber_delta;
+      if (st->loss == DEXR_LOSS_POSITION) {
+        v = T.w * (huber_val(fabsf(rx), beta, inv_beta) + huber_val(fabsf(ry), beta, inv_beta) +
+                   huber_val(fabsf(rz), beta, inv_beta));
+      } else {
+        v = T.w * huber_val(sqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz))), beta, inv_beta);
+      }
+    }
+    if (var >= 0) {
+      const float dx = xv - x0;
+      v = fmaf(prm.norm_delta * dx, dx, v);
+    }
+    return gsum<G>(v);
+  }
+
+  // Per-frame targets and weights -> fr[k]; DexPilot flag update (optimizer.py:460-508).
+  // Returns false if an input is non finite.
+  __device__ __forceinline__ bool prepare_targets(const FrameInputs& in, bool active) {
+    const int m = st->n_res;
+    const int loss = st->loss;
+    float tx = 0.f, ty = 0.f, tz = 0.f, w = 0.f;
+    if (active && l < m) {
+      if (in.kp != nullptr) {
+        const int ht = st->res_ht[l], ho = st->res_ho[l];
+        tx = in.kp[3 * ht]; ty = in.kp[3 * ht + 1]; tz = in.kp[3 * ht + 2];
+        if (ho >= 0) { tx -= in.kp[3 * ho]; ty -= in.kp[3 * ho + 1]; tz -= in.kp[3 * ho + 2]; }
+      } else {
+        tx = in.ref[3 * l]; ty = in.ref[3 * l + 1]; tz = in.ref[3 * l + 2];
+      }
+    }
+    bool finite = isfinite(tx) && isfinite(ty) && isfinite(tz);
+    if (loss == DEXR_LOSS_POSITION) {
+      w = 1.0f / (3.0f * m);
+    } else if (loss == DEXR_LOSS_VECTOR) {
+      tx *= prm.scaling; ty *= prm.scaling; tz *= prm.scaling;
+      w = 1.0f / m;
+    } else {
+      const int len_proj = st->len_proj, len_s1 = st->len_s1;
+      const float dist = sqrtf(fmaf(tx, tx, fmaf(ty, ty, tz * tz)));
+      int flag = 0;
+      if (l < len_s1) {
+        flag = (active && in.projected != nullptr) ? in.projected[l] : 0;
+        if (dist < prm.project_dist) flag = 1;
+        if (dist > prm.escape_dist) flag = 0;
+      }
+      const int k2 = l - len_s1;
+      const bool is_s2 = (l >= len_s1) && (l < len_proj);
+      const int so = is_s2 ? st->s2_origin[k2] : 0, sk = is_s2 ? st->s2_task[k2] : 0;
+      const int fo = gshfl_i<G>(flag, so), fk_ = gshfl_i<G>(flag, sk);
+      if (is_s2) flag = (fo && fk_ && dist <= 0.03f) ? 1 : 0;
+      float weight;
+      if (l < len_proj) {
+        weight = flag ? (l < len_s1 ? 200.0f : 400.0f) : 1.0f;
+        if (flag) {
+          const float sc_ = (l < len_s1 ? prm.eta1 : prm.eta2) / (dist + 1e-6f);
+          tx *= sc_; ty *= sc_; tz *= sc_;
+        } else {
+          tx *= prm.scaling; ty *= prm.scaling; tz *= prm.scaling;
+        }
+        if (active && in.projected != nullptr) in.projected[l] = (uint8_t)flag;
+      } else {
+        weight = (float)(len_proj + st->num_fingers);
+        tx *= prm.scaling; ty *= prm.scaling; tz *= prm.scaling;
+      }
+      w = weight / m;
+    }
+    if (l < m) fr()[l] = make_float4(tx, ty, tz, w);
+    return !gany<G>(!finite, lane);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // One frame.  Returns status word.  On exit x (var lanes) and q (all lanes) hold the solution.
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ int solve(const FrameInputs& in, bool active) {
+    const int dof = st->dof;
+    const float nd = prm.norm_delta;
+    const float beta = prm.huber_delta;
+    int status = 0;
+
+    // ---- prelude: warm start, anchor, fixed joints (optimizer.py:138-141, seq_retarget.py:115-121)
+    float xin = 0.f;
+    if (in.last == nullptr) xin = var >= 0 ? x : 0.f;  // sequences: previous solution kept in registers
+    else if (active && var >= 0) xin = in.last[var];
+    if (prm.clip_init && var >= 0) xin = fminf(fmaxf(xin, clo), chi);
+    x0 = xin;
+    x = fminf(fmaxf(xin, lo), hi);
+    qfix = (active && fixedi >= 0) ? in.fixed[fixedi] : 0.f;
+    bool finite = isfinite(xin) && isfinite(qfix);
+    const bool ok_in = prepare_targets(in, active);
+    finite = !gany<G>(!finite, lane) && ok_in;
+    __syncwarp();
+    if (!finite) {
+      status |= DEXR_STATUS_NONFINITE;
+      x = x0;
+      if (!isfinite(x)) x = 0.f;
+      if (!isfinite(qfix)) qfix = 0.f;
+      active = false;
+    }
+    q = compose_q(x);
+    fk(q, R, p);
+    cur = 0;
+    write_links(R, p, cur);
+    __syncwarp();
+    F = cost(cur, x);
+
+    float lam = prm.lambda0;
+    int iters = 0, rejects = 0;
+    bool done = !active;
+
+    while (gany<32>(!done, lane)) {
+      // ======================= gradient + exact Hessian at x ===========================
+      float H[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) H[i] = 0.f;
+      float g = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      a[0] = fmaf(R[0], ax[0], fmaf(R[1], ax[1], R[2] * ax[2]));
+      a[1] = fmaf(R[3], ax[0], fmaf(R[4], ax[1], R[5] * ax[2]));
+      a[2] = fmaf(R[6], ax[0], fmaf(R[7], ax[1], R[8] * ax[2]));
+      const bool rev = jtype == 0;
+      const int m = st->n_res;
+      const int loss = st->loss;
+      const float4* lpc = lp(cur);
+      for (int k = 0; k < m; ++k) {
+        const int ti = st->res_task[k], oi = st->res_origin[k];
+        const float4 T = fr()[k];
+        const float4 pt = lpc[ti];
+        const uint32_t mt = st->link_anc[ti];
+        float rx = pt.x - T.x, ry = pt.y - T.y, rz = pt.z - T.z;
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+        if ((mt >> l) & 1u) {
+          if (rev) {
+            const float dx = pt.x - p[0], dy = pt.y - p[1], dz = pt.z - p[2];
+            j0 = a[1] * dz - a[2] * dy; j1 = a[2] * dx - a[0] * dz; j2 = a[0] * dy - a[1] * dx;
+          } else { j0 = a[0]; j1 = a[1]; j2 = a[2]; }
+        }
+        uint32_t mo = 0u;
+        if (oi >= 0) {
+          const float4 po = lpc[oi];
+          mo = st->link_anc[oi];
+          rx -= po.x; ry -= po.y; rz -= po.z;
+          if ((mo >> l) & 1u) {
+            if (rev) {
+              const float dx = po.x - p[0], dy = po.y - p[1], dz = po.z - p[2];
+              j0 -= a[1] * dz - a[2] * dy; j1 -= a[2] * dx - a[0] * dz; j2 -= a[0] * dy - a[1] * dx;
+            } else { j0 -= a[0]; j1 -= a[1]; j2 -= a[2]; }
+          }
+        }
+        // loss derivatives wrt the residual block (uniform across lanes)
+        float gx, gy, gz, y0, y1, y2;
+        if (loss == DEXR_LOSS_POSITION) {
+          const bool qx = fabsf(rx) < beta, qy = fabsf(ry) < beta, qz = fabsf(rz) < beta;
+          gx = T.w * (qx ? rx * inv_beta : copysignf(1.f, rx));
+          gy = T.w * (qy ? ry * inv_beta : copysignf(1.f, ry));
+          gz = T.w * (qz ? rz * inv_beta : copysignf(1.f, rz));
+          y0 = qx ? T.w * inv_beta * j0 : 0.f;
+          y1 = qy ? T.w * inv_beta * j1 : 0.f;
+          y2 = qz ? T.w * inv_beta * j2 : 0.f;
+        } else {
+          const float d = sqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
+          const bool quad = d < beta;
+          const float invd = d > 0.f ? 1.0f / d : 0.f;
+          const float ux = rx * invd, uy = ry * invd, uz = rz * invd;
+          const float hp = quad ? d * inv_beta : 1.0f;
+          gx = T.w * hp * ux; gy = T.w * hp * uy; gz = T.w * hp * uz;
+          const float s_iso = T.w * (quad ? inv_beta : invd);
+          const float s_rad = quad ? 0.f : T.w * invd;
+          const float uj = s_rad * fmaf(ux, j0, fmaf(uy, j1, uz * j2));
+          y0 = fmaf(s_iso, j0, -uj * ux); y1 = fmaf(s_iso, j1, -uj * uy); y2 = fmaf(s_iso, j2, -uj * uz);
+        }
+        g = fmaf(j0, gx, fmaf(j1, gy, fmaf(j2, gz, g)));
+        t0 += j1 * gz - j2 * gy; t1 += j2 * gx - j0 * gz; t2 += j0 * gy - j1 * gx;
+        const int b = k & 1;
+        jbuf(b, 0)[l] = j0; jbuf(b, 1)[l] = j1; jbuf(b, 2)[l] = j2;
+        __syncwarp();
+        const uint32_t cols = mt | mo;
+#pragma unroll
+        for (int blk = 0; blk < NP / 4; ++blk) {
+          if ((cols >> (4 * blk)) & 0xFu) {
+            const float4 c0 = *reinterpret_cast<const float4*>(jbuf(b, 0) + 4 * blk);
+            const float4 c1 = *reinterpret_cast<const float4*>(jbuf(b, 1) + 4 * blk);
+            const float4 c2 = *reinterpret_cast<const float4*>(jbuf(b, 2) + 4 * blk);
+            H[4 * blk + 0] = fmaf(c0.x, y0, fmaf(c1.x, y1, fmaf(c2.x, y2, H[4 * blk + 0])));
+            H[4 * blk + 1] = fmaf(c0.y, y0, fmaf(c1.y, y1, fmaf(c2.y, y2, H[4 * blk + 1])));
+            H[4 * blk + 2] = fmaf(c0.z, y0, fmaf(c1.z, y1, fmaf(c2.z, y2, H[4 * blk + 2])));
+            H[4 * blk + 3] = fmaf(c0.w, y0, fmaf(c1.w, y1, fmaf(c2.w, y2, H[4 * blk + 3])));
+          }
+        }
+      }
+      // ---- FK curvature: S[i][c] = a_i . t_c (i ancestor-or-self of c), symmetric otherwise ----
+      {
+        const float ar0 = rev ? a[0] : 0.f, ar1 = rev ? a[1] : 0.f, ar2 = rev ? a[2] : 0.f;
+        at()[2 * l] = make_float4(ar0, ar1, ar2, 0.f);
+        at()[2 * l + 1] = make_float4(t0, t1, t2, 0.f);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          if (i < dof) {
+            const float4 ai = at()[2 * i];
+            const float4 ti_ = at()[2 * i + 1];
+            const bool up = (anc >> i) & 1u;
+            const bool dn = (desc >> i) & 1u;
+            const float vu = fmaf(ai.x, t0, fmaf(ai.y, t1, ai.z * t2));
+            const float vd = fmaf(ar0, ti_.x, fmaf(ar1, ti_.y, ar2 * ti_.z));
+            H[i] += up ? vu : (dn ? vd : 0.f);
+          }
+        }
+      }
+      // ---- mimic fold: H_x = M^T H_q M, g_x = M^T g_q (kinematics_adaptor.py:107-113) ----
+      if (st->has_mimic) {
+        const float ml = var >= 0 ? 1.0f : (msrc >= 0 ? mmult : 0.f);
+        float* hbuf = hb();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = ml * H[i];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) H[i] = 0.f;
+        for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
+          if (var >= 0 && f < gcount) {
+            const int cl = glane[f];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) H[i] += hbuf[i * NP + cl];
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+          float acc = 0.f;
+          if (s < dof) {
+            const int cnt = st->group_count[s];
+            for (int f = 0; f < cnt; ++f) acc = fmaf(st->group_mult[s][f], hbuf[st->group_lane[s][f] * NP + l], acc);
+          }
+          H[s] = acc;
+        }
+        float gx_ = 0.f;
+#pragma unroll
+        for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
+          const bool v = var >= 0 && f < gcount;
+          const float gv = gshfl<G>(g, v ? glane[f] : l);
+          if (v) gx_ = fmaf(gmult[f], gv, gx_);
+        }
+        g = gx_;
+        __syncwarp();
+      }
+      // ---- regulariser, active set (box bounds), freeze ----
+      const bool isvar = var >= 0;
+      g = isvar ? fmaf(2.0f * nd, x - x0, g) : 0.f;
+      const bool act = isvar && ((x <= lo && g > 0.f) || (x >= hi && g < 0.f));
+      const bool free_ = isvar && !act;
+      const unsigned fmask = gballot<G>(free_, lane);
+      float hd = 1.0f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const bool keep = free_ && ((fmask >> i) & 1u);
+        float v = keep ? H[i] : 0.f;
+        if (i == l) { v = free_ ? v + 2.0f * nd : 1.0f; hd = v; }
+        H[i] = v;
+      }
+      if (!free_) g = 0.f;
+      const float D = fabsf(hd) + 1e-6f;
+      {
+        float* hbuf = hb();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
+      }
+      // ======================= damped Newton trials ====================================
+      bool accepted = done;
+      float Rn[9], pn[3];
+      for (int trial = 0; trial < kMaxTrials; ++trial) {
+        if (!gany<32>(!accepted, lane)) break;
+        if (trial > 0) {
+          const float* hbuf = hb();
+#pragma unroll
+          for (int i = 0; i < NP; ++i) H[i] = hbuf[i * NP + l];
+        }
+        float y = -g;
+        float myinv = 1.0f;
+        bool bad = false;
+        float* Lr = lrow();
+        float* Lc = lcol();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          if (k < dof) {
+            float hk = H[k];
+            if (k == l) hk = fmaf(lam, D, hk);
+            const float dkk = gshfl<G>(hk, k);
+            bad = bad || !(dkk > 1e-20f);
+            const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
+            const float lik = hk * inv;
+            const float yk = gshfl<G>(y, k) * inv;
+            if (l == k) { myinv = inv; y = yk; }
+            if (l > k) y = fmaf(-lik, yk, y);
+            Lr[k * NP + l] = lik;
+            Lc[k * (NP + 1) + l] = lik;
+            __syncwarp();
+#pragma unroll
+            for (int j0 = ((k + 1) / 4) * 4; j0 < NP; j0 += 4) {
+              if (j0 < dof) {
+                const float4 lj = *reinterpret_cast<const float4*>(Lr + k * NP + j0);
+                if (j0 + 0 > k) H[j0 + 0] = fmaf(-lik, lj.x, H[j0 + 0]);
+                if (j0 + 1 > k) H[j0 + 1] = fmaf(-lik, lj.y, H[j0 + 1]);
+                if (j0 + 2 > k) H[j0 + 2] = fmaf(-lik, lj.z, H[j0 + 2]);
+                if (j0 + 3 > k) H[j0 + 3] = fmaf(-lik, lj.w, H[j0 + 3]);
+              }
+            }
+          }
+        }
+        // back substitution: L^T delta = y
+#pragma unroll
+        for (int k = NP - 1; k >= 0; --k) {
+          if (k < dof) {
+            const float xk = gshfl<G>(y * myinv, k);
+            if (l == k) y = xk;
+            if (l < k) y = fmaf(-Lc[l * (NP + 1) + k], xk, y);
+          }
+        }
+        bad = gany<G>(bad || !isfinite(y), lane);
+        float xn = free_ ? fminf(fmaxf(x + y, lo), hi) : x;
+        if (bad) xn = x;
+        const float dx = xn - x;
+        const float step = gmax<G>(fabsf(dx));
+        const float pred = 0.5f * gsum<G>(dx * fmaf(lam * D, dx, -g));
+        const float qn = compose_q(xn);
+        fk(qn, Rn, pn);
+        write_links(Rn, pn, cur ^ 1);
+        __syncwarp();
+        const float Fn = cost(cur ^ 1, xn);
+        const bool ok = !bad && isfinite(Fn) && (Fn <= F || step < prm.tol || pred < kNoise * fabsf(F));
+        if (!accepted) {
+          if (ok) {
+            x = xn; q = qn; F = Fn;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) p[i] = pn[i];
+            cur ^= 1;
+            lam = fmaxf(lam * kLamDown, kLamMin);
+            accepted = true;
+            if (step < prm.tol) done = true;
+          } else {
+            lam *= kLamUp;
+            ++rejects;
+          }
+        }
+        __syncwarp();
+      }
+      if (!done) {
+        if (!accepted) done = true;  // no descent direction left at fp32 resolution
+        ++iters;
+        if (iters >= prm.max_iters && !done) { done = true; status |= DEXR_STATUS_MAXITER; }
+      }
+    }
+    status |= (iters & 0xffff) | ((rejects > 255 ? 255 : rejects) << 16);
+    return status;
+  }
+};
+
+}  // namespace dexr

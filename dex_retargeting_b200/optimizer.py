@@ -1,0 +1,428 @@
+"""Position / Vector / DexPilot optimizers backed by the sm_100a solver (libdexr.so).
+
+Drop-in for `dex_retargeting.optimizer` (reference: src/dex_retargeting/optimizer.py:15-577): same
+class names, constructor arguments, attributes (`idx_pin2target`, `idx_pin2fixed`,
+`target_link_human_indices`, `computed_link_indices`, `origin_link_indices`, ...), the same
+`retarget(ref_value, fixed_qpos, last_qpos) -> float32 (n,)` entry, the same ValueErrors.
+
+What changed underneath: there is no nlopt object and no Python objective closure.  `retarget()` ships
+one frame through the C ABI (`dexr_solve_frames_host`); the new `retarget_batch()` takes torch CUDA
+tensors `[B, ...]` and solves every frame of the batch in ONE kernel launch (`dexr_solve_frames`).
+The solver minimises the objective whose gradient the reference hands to SLSQP, i.e.
+    L(x) + norm_delta * |x - last_qpos|^2      inside [lower - 1e-3, upper + 1e-3]
+to convergence (the reference stops SLSQP early at ftol_abs 1e-5 / 1e-6, optimizer.py:136,239,397).
+There is no CPU fallback: without the CUDA library / a GPU these calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from abc import abstractmethod
+from typing import List, Optional
+
+import numpy as np
+
+from . import _native as N
+from .kinematics_adaptor import KinematicAdaptor, MimicJointKinematicAdaptor
+from .robot_wrapper import RobotWrapper
+from .table import ObjectiveSpec, compile_table, table_bytes
+
+
+class _SolverStats:
+    """Stand-in for the attributes of `nlopt.opt` that callers read (seq_retarget.py:147-152)."""
+
+    def __init__(self):
+        self._value = float("nan")
+
+    def last_optimum_value(self):
+        return self._value
+
+
+class _Engine:
+    """Owns one `dexr_robot_t` handle (device copy of a robot table)."""
+
+    def __init__(self, table: N.DexrTable, device: int, table_dev_ptr: Optional[int] = None):
+        self.lib = N.load()
+        self.table = table
+        self.device = int(device)
+        h = C.c_void_p()
+        if table_dev_ptr is None:
+            N.check(self.lib.dexr_robot_create(C.byref(table), self.device, C.byref(h)), "dexr_robot_create")
+        else:
+            N.check(self.lib.dexr_robot_create_from_device(C.c_void_p(table_dev_ptr), C.sizeof(N.DexrTable), self.device,
+                                                            C.byref(h)), "dexr_robot_create_from_device")
+        self.handle = h
+
+    def launch_info(self) -> dict:
+        info = N.DexrLaunchInfo()
+        N.check(self.lib.dexr_get_launch_info(self.handle, C.byref(info)), "dexr_get_launch_info")
+        return {k: getattr(info, k) for k, _ in info._fields_}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dexr_robot_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _default_device() -> int:
+    import torch
+
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
+class Optimizer:
+    retargeting_type = "BASE"
+
+    def __init__(self, robot: RobotWrapper, target_joint_names: List[str], target_link_human_indices: np.ndarray,
+                 device: Optional[int] = None):
+        self.robot = robot
+        self.num_joints = robot.dof
+
+        joint_names = robot.dof_joint_names
+        idx_pin2target = []
+        for name in target_joint_names:
+            if name not in joint_names:
+                raise ValueError(f"Joint {name} given does not appear to be in robot XML.")
+            idx_pin2target.append(joint_names.index(name))
+        self.target_joint_names = list(target_joint_names)
+        self.idx_pin2target = np.array(idx_pin2target)
+        self.idx_pin2fixed = np.array([i for i in range(robot.dof) if i not in idx_pin2target], dtype=int)
+        self.opt_dof = len(idx_pin2target)  # includes nothing but the optimised joints
+        self.opt = _SolverStats()
+
+        self.target_link_human_indices = target_link_human_indices
+        self.has_free_joint = len([n for n in robot.link_names if "dummy" in n]) >= 6
+        self.adaptor: Optional[KinematicAdaptor] = None
+
+        # bounds: "no limit" until set_joint_limit is called (SeqRetargeting does, seq_retarget.py:22-31)
+        self._limits = np.tile(np.array([[-1e4, 1e4]]), (self.opt_dof, 1))
+        self._epsilon = 1e-3
+        self._device = device
+        self._engine: Optional[_Engine] = None
+        # solver knobs that have no counterpart in the reference
+        self.max_iters = 64
+        self.step_tol = 1e-5
+        self.lambda0 = 1e-3
+
+    # ---------------------------------------------------------------- reference API
+    def set_joint_limit(self, joint_limits: np.ndarray, epsilon=1e-3):
+        joint_limits = np.asarray(joint_limits)
+        if joint_limits.shape != (self.opt_dof, 2):
+            raise ValueError(f"Expect joint limits have shape: {(self.opt_dof, 2)}, but get {joint_limits.shape}")
+        self._limits = joint_limits.astype(np.float64).copy()
+        self._epsilon = float(epsilon)
+        self._engine = None
+
+    def get_link_indices(self, target_link_names):
+        return [self.robot.get_link_index(n) for n in target_link_names]
+
+    def set_kinematic_adaptor(self, adaptor: KinematicAdaptor):
+        self.adaptor = adaptor
+        if isinstance(adaptor, MimicJointKinematicAdaptor):  # mimic joints are driven, not supplied
+            mimic = set(int(i) for i in adaptor.idx_pin2mimic)
+            self.idx_pin2fixed = np.array([x for x in self.idx_pin2fixed if int(x) not in mimic], dtype=int)
+        self._engine = None
+
+    @property
+    def fixed_joint_names(self):
+        names = self.robot.dof_joint_names
+        return [names[i] for i in self.idx_pin2fixed]
+
+    def retarget(self, ref_value, fixed_qpos, last_qpos):
+        """One frame.  ref_value: (m,3); fixed_qpos: (len(idx_pin2fixed),); last_qpos: (opt_dof,) warm start
+        and regularisation anchor.  Returns float32 (opt_dof,) in `target_joint_names` order."""
+        if len(fixed_qpos) != len(self.idx_pin2fixed):
+            raise ValueError(
+                f"Optimizer has {len(self.idx_pin2fixed)} joints but non_target_qpos {fixed_qpos} is given"
+            )
+        qpos, _ = self._solve_host(np.asarray(ref_value, dtype=np.float32)[None], np.asarray(fixed_qpos, dtype=np.float32)[None],
+                                   np.asarray(last_qpos, dtype=np.float32)[None], clip_init=False)
+        return qpos[0]
+
+    # ---------------------------------------------------------------- engine
+    @abstractmethod
+    def _objective_spec(self) -> ObjectiveSpec:
+        ...
+
+    def _loss_params(self, p: N.DexrParams):
+        """Fill the loss-specific fields of the parameter block."""
+
+    def _mimic_tuple(self):
+        a = self.adaptor
+        if isinstance(a, MimicJointKinematicAdaptor):
+            return (a.source_joint_names, a.mimic_joint_names, [float(v) for v in a.multipliers], [float(v) for v in a.offsets])
+        return None
+
+    def build_table(self) -> N.DexrTable:
+        return compile_table(self.robot.kin, self.target_joint_names, self._objective_spec(), self._limits,
+                             self._epsilon, self._mimic_tuple(), self.fixed_joint_names)
+
+    @property
+    def device_index(self) -> int:
+        if self._device is None:
+            self._device = _default_device()
+        return int(self._device)
+
+    def engine(self) -> _Engine:
+        if self._engine is None:
+            self._engine = _Engine(self.build_table(), self.device_index)
+        return self._engine
+
+    def adopt_device_table(self, table: N.DexrTable, table_dev_ptr: int, device: int):
+        """Use a table that already lives on `device` (after an NCCL broadcast, see parallel.py)."""
+        self._device = device
+        self._engine = _Engine(table, device, table_dev_ptr)
+
+    def params(self, clip_init: bool = False, lp_alpha: float = -1.0) -> N.DexrParams:
+        p = N.default_params()
+        p.tol, p.lambda0, p.max_iters = self.step_tol, self.lambda0, int(self.max_iters)
+        p.clip_init = 1 if clip_init else 0
+        p.lp_alpha = float(lp_alpha)
+        self._loss_params(p)
+        return p
+
+    @property
+    def num_residuals(self) -> int:
+        return len(self._objective_spec().res_task)
+
+    # ---------------------------------------------------------------- host path (numpy, B small)
+    def _solve_host(self, ref_value, fixed_qpos, last_qpos, clip_init, keypoints=None, projected=None,
+                    want_robot_qpos=False):
+        eng = self.engine()
+        B = last_qpos.shape[0]
+        n = self.opt_dof
+        m = self.num_residuals
+        io = N.DexrFrames()
+        keep = []
+
+        def ptr(a):
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        if keypoints is not None:
+            kp = np.ascontiguousarray(keypoints, dtype=np.float32).reshape(B, N.NUM_KEYPOINTS, 3)
+            io.keypoints = ptr(kp)
+        else:
+            rv = np.ascontiguousarray(ref_value, dtype=np.float32)
+            if rv.shape != (B, m, 3):
+                raise ValueError(f"ref_value must have shape {(m, 3)}, got {rv.shape[1:]}")
+            io.ref_value = ptr(rv)
+        lq = np.ascontiguousarray(last_qpos, dtype=np.float32).reshape(B, n)
+        io.last_qpos = ptr(lq)
+        nf = len(self.idx_pin2fixed)
+        if nf:
+            io.fixed_qpos = ptr(np.ascontiguousarray(fixed_qpos, dtype=np.float32).reshape(B, nf))
+        qpos = np.empty((B, n), dtype=np.float32)
+        cost = np.empty((B,), dtype=np.float32)
+        status = np.empty((B,), dtype=np.int32)
+        io.qpos_out, io.cost_out, io.status_out = ptr(qpos), ptr(cost), ptr(status)
+        rq = None
+        if want_robot_qpos:
+            rq = np.empty((B, self.robot.dof), dtype=np.float32)
+            io.robot_qpos_out = ptr(rq)
+        if projected is not None:
+            io.projected = ptr(projected)
+        p = self.params(clip_init=clip_init)
+        N.check(eng.lib.dexr_solve_frames_host(eng.handle, C.byref(p), C.byref(io), B), "dexr_solve_frames_host")
+        self.opt._value = float(cost[-1])
+        self.last_status = status
+        return qpos, rq
+
+    # ---------------------------------------------------------------- device path (torch, B large)
+    def retarget_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
+                       out=None, robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None):
+        """Solve B independent frames in one launch.  All arguments are float32 CUDA tensors on this
+        optimizer's device (projected: uint8, status_out: int32), contiguous:
+          ref_value [B,m,3]  OR  keypoints [B,21,3] (the human-index gather is done in the kernel)
+          fixed_qpos [B,len(idx_pin2fixed)] (omit when there are none), last_qpos [B,opt_dof]
+        Returns qpos [B,opt_dof] (= `out` if given).  Nothing is synchronised."""
+        import torch
+
+        eng = self.engine()
+        if last_qpos is None:
+            raise ValueError("last_qpos is required")
+        B = last_qpos.shape[0]
+        dev = torch.device("cuda", eng.device)
+
+        def chk(t, shape, dtype, name):
+            if t.device != dev or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected contiguous {dtype} tensor of shape {tuple(shape)} on {dev}, "
+                                 f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+            return t.data_ptr()
+
+        io = N.DexrFrames()
+        m = self.num_residuals
+        if (ref_value is None) == (keypoints is None):
+            raise ValueError("give exactly one of ref_value / keypoints")
+        if keypoints is not None:
+            io.keypoints = chk(keypoints, (B, N.NUM_KEYPOINTS, 3), torch.float32, "keypoints")
+        else:
+            io.ref_value = chk(ref_value, (B, m, 3), torch.float32, "ref_value")
+        io.last_qpos = chk(last_qpos, (B, self.opt_dof), torch.float32, "last_qpos")
+        nf = len(self.idx_pin2fixed)
+        if nf:
+            if fixed_qpos is None:
+                raise ValueError(f"Optimizer has {nf} joints but no fixed_qpos is given")
+            io.fixed_qpos = chk(fixed_qpos, (B, nf), torch.float32, "fixed_qpos")
+        if out is None:
+            out = torch.empty((B, self.opt_dof), dtype=torch.float32, device=dev)
+        io.qpos_out = chk(out, (B, self.opt_dof), torch.float32, "out")
+        if robot_qpos_out is not None:
+            io.robot_qpos_out = chk(robot_qpos_out, (B, self.robot.dof), torch.float32, "robot_qpos_out")
+        if status_out is not None:
+            io.status_out = chk(status_out, (B,), torch.int32, "status_out")
+        if cost_out is not None:
+            io.cost_out = chk(cost_out, (B,), torch.float32, "cost_out")
+        if projected is not None:
+            io.projected = chk(projected, (B, self._objective_spec().len_proj), torch.uint8, "projected")
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        p = self.params(clip_init=clip_init)
+        N.check(eng.lib.dexr_solve_frames(eng.handle, C.byref(p), C.byref(io), B, C.c_void_p(s.cuda_stream)),
+                "dexr_solve_frames")
+        return out
+
+
+class PositionOptimizer(Optimizer):
+    retargeting_type = "POSITION"
+
+    def __init__(self, robot: RobotWrapper, target_joint_names: List[str], target_link_names: List[str],
+                 target_link_human_indices: np.ndarray, huber_delta=0.02, norm_delta=4e-3, device=None):
+        super().__init__(robot, target_joint_names, target_link_human_indices, device)
+        self.body_names = target_link_names
+        self.huber_delta = huber_delta
+        self.norm_delta = norm_delta
+        self.target_link_indices = self.get_link_indices(target_link_names)  # also the name check
+
+    def _objective_spec(self) -> ObjectiveSpec:
+        idx = [int(i) for i in np.asarray(self.target_link_human_indices).reshape(-1)]
+        m = len(self.body_names)
+        if len(idx) != m:
+            raise ValueError("Position retargeting link names and link indices dim mismatch")
+        return ObjectiveSpec(N.LOSS_POSITION, list(self.body_names), list(range(m)), [-1] * m, idx, [-1] * m)
+
+    def _loss_params(self, p):
+        p.huber_delta, p.norm_delta, p.scaling = self.huber_delta, self.norm_delta, 1.0
+
+
+def _link_cache(origin_names, task_names):
+    """Positions of a link shared by several vectors are computed once (optimizer.py:224-234)."""
+    computed = list(dict.fromkeys(list(origin_names) + list(task_names)))
+    return computed, [computed.index(n) for n in origin_names], [computed.index(n) for n in task_names]
+
+
+class VectorOptimizer(Optimizer):
+    retargeting_type = "VECTOR"
+
+    def __init__(self, robot: RobotWrapper, target_joint_names: List[str], target_origin_link_names: List[str],
+                 target_task_link_names: List[str], target_link_human_indices: np.ndarray, huber_delta=0.02,
+                 norm_delta=4e-3, scaling=1.0, device=None):
+        super().__init__(robot, target_joint_names, target_link_human_indices, device)
+        self.origin_link_names = target_origin_link_names
+        self.task_link_names = target_task_link_names
+        self.huber_delta = huber_delta
+        self.norm_delta = norm_delta
+        self.scaling = scaling
+        self.computed_link_names, origin_idx, task_idx = _link_cache(target_origin_link_names, target_task_link_names)
+        self.origin_link_indices = np.array(origin_idx)
+        self.task_link_indices = np.array(task_idx)
+        self.computed_link_indices = self.get_link_indices(self.computed_link_names)
+
+    def _objective_spec(self) -> ObjectiveSpec:
+        hi = np.asarray(self.target_link_human_indices)
+        return ObjectiveSpec(N.LOSS_VECTOR, list(self.computed_link_names), [int(i) for i in self.task_link_indices],
+                             [int(i) for i in self.origin_link_indices], [int(i) for i in hi[1]], [int(i) for i in hi[0]])
+
+    def _loss_params(self, p):
+        p.huber_delta, p.norm_delta, p.scaling = self.huber_delta, self.norm_delta, self.scaling
+
+
+class DexPilotOptimizer(Optimizer):
+    """DexPilot-style retargeting (https://arxiv.org/abs/1910.03135) for 2 to 5 fingers: finger-pair
+    vectors are pulled together once the human thumb/finger distance drops below `project_dist` and
+    released above `escape_dist`; wrist-to-tip vectors carry a larger weight."""
+
+    retargeting_type = "DEXPILOT"
+
+    def __init__(self, robot: RobotWrapper, target_joint_names: List[str], finger_tip_link_names: List[str],
+                 wrist_link_name: str, target_link_human_indices: Optional[np.ndarray] = None, huber_delta=0.03,
+                 norm_delta=4e-3, project_dist=0.03, escape_dist=0.05, eta1=1e-4, eta2=3e-2, scaling=1.0, device=None):
+        if len(finger_tip_link_names) < 2 or len(finger_tip_link_names) > 5:
+            raise ValueError(
+                f"DexPilot optimizer can only be applied to hands with 2 to 5 fingers, but got "
+                f"{len(finger_tip_link_names)} fingers."
+            )
+        self.num_fingers = len(finger_tip_link_names)
+        origin_link_index, task_link_index = self.generate_link_indices(self.num_fingers)
+        if target_link_human_indices is None:
+            target_link_human_indices = (np.stack([origin_link_index, task_link_index], axis=0) * 4).astype(int)
+        link_names = [wrist_link_name] + list(finger_tip_link_names)
+        origin_names = [link_names[i] for i in origin_link_index]
+        task_names = [link_names[i] for i in task_link_index]
+
+        super().__init__(robot, target_joint_names, target_link_human_indices, device)
+        self.origin_link_names = origin_names
+        self.task_link_names = task_names
+        self.scaling = scaling
+        self.huber_delta = huber_delta
+        self.norm_delta = norm_delta
+        self.project_dist = project_dist
+        self.escape_dist = escape_dist
+        self.eta1 = eta1
+        self.eta2 = eta2
+        self.computed_link_names, origin_idx, task_idx = _link_cache(origin_names, task_names)
+        self.origin_link_indices = np.array(origin_idx)
+        self.task_link_indices = np.array(task_idx)
+        self.computed_link_indices = self.get_link_indices(self.computed_link_names)
+        (self.projected, self.s2_project_index_origin, self.s2_project_index_task, self.projected_dist) = (
+            self.set_dexpilot_cache(self.num_fingers, eta1, eta2)
+        )
+
+    @staticmethod
+    def generate_link_indices(num_fingers):
+        """
+        >>> DexPilotOptimizer.generate_link_indices(4)
+        ([2, 3, 4, 3, 4, 4, 0, 0, 0, 0], [1, 1, 1, 2, 2, 3, 1, 2, 3, 4])
+        """
+        pairs = [(j, i) for i in range(1, num_fingers) for j in range(i + 1, num_fingers + 1)]
+        pairs += [(0, i) for i in range(1, num_fingers + 1)]  # wrist (0) -> every finger tip
+        return [o for o, _ in pairs], [t for _, t in pairs]
+
+    @staticmethod
+    def set_dexpilot_cache(num_fingers, eta1, eta2):
+        """
+        >>> DexPilotOptimizer.set_dexpilot_cache(4, 0.1, 0.2)
+        (array([False, False, False, False, False, False]), [1, 2, 2], [0, 0, 1], array([0.1, 0.1, 0.1, 0.2, 0.2, 0.2]))
+        """
+        n_s1 = num_fingers - 1
+        s2 = [(j, i) for i in range(0, num_fingers - 2) for j in range(i + 1, num_fingers - 1)]
+        projected = np.zeros(n_s1 + len(s2), dtype=bool)
+        projected_dist = np.array([eta1] * n_s1 + [eta2] * len(s2))
+        return projected, [o for o, _ in s2], [t for _, t in s2], projected_dist
+
+    def _objective_spec(self) -> ObjectiveSpec:
+        hi = np.asarray(self.target_link_human_indices)
+        len_proj = len(self.projected)
+        len_s2 = len(self.s2_project_index_task)
+        return ObjectiveSpec(
+            N.LOSS_DEXPILOT, list(self.computed_link_names), [int(i) for i in self.task_link_indices],
+            [int(i) for i in self.origin_link_indices], [int(i) for i in hi[1]], [int(i) for i in hi[0]],
+            num_fingers=self.num_fingers, len_proj=len_proj, len_s1=len_proj - len_s2,
+            s2_origin=list(self.s2_project_index_origin), s2_task=list(self.s2_project_index_task),
+        )
+
+    def _loss_params(self, p):
+        p.huber_delta, p.norm_delta, p.scaling = self.huber_delta, self.norm_delta, self.scaling
+        p.project_dist, p.escape_dist, p.eta1, p.eta2 = self.project_dist, self.escape_dist, self.eta1, self.eta2
+
+    def retarget(self, ref_value, fixed_qpos, last_qpos):
+        if len(fixed_qpos) != len(self.idx_pin2fixed):
+            raise ValueError(
+                f"Optimizer has {len(self.idx_pin2fixed)} joints but non_target_qpos {fixed_qpos} is given"
+            )
+        flags = np.ascontiguousarray(self.projected, dtype=np.uint8)[None]  # hysteresis state, updated in place
+        qpos, _ = self._solve_host(np.asarray(ref_value, dtype=np.float32)[None], np.asarray(fixed_qpos, dtype=np.float32)[None],
+                                   np.asarray(last_qpos, dtype=np.float32)[None], clip_init=False, projected=flags)
+        self.projected = flags[0].astype(bool)
+        return qpos[0]
