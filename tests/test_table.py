@@ -1,0 +1,150 @@
+"""Robot-table compiler: every reference config compiles; the table's pointer-jumping FK, ancestor masks,
+mimic groups and index maps reproduce the float64 model."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import build_oracle, build_product, configs
+from dex_retargeting_b200 import _native as N
+from dex_retargeting_b200.table import table_bytes, table_from_bytes
+
+ALL_KEYS = sorted(configs())
+
+
+def emulate_table_fk(t, q):
+    """What the kernel does (dexr_kernels.cuh Solver::fk), in float64 numpy, driven ONLY by the table."""
+    dof = t.dof
+    R, p = [], []
+    for c in range(dof):
+        R0, RA, RB = (np.array(x[c][:]).reshape(3, 3) for x in (t.R0, t.RA, t.RB))
+        p0, d0 = np.array(t.p0[c][:]), np.array(t.d0[c][:])
+        if t.jtype[c] == 0:
+            R.append(R0 + np.sin(q[c]) * RA + (1 - np.cos(q[c])) * RB)
+            p.append(p0.copy())
+        else:
+            R.append(R0.copy())
+            p.append(p0 + q[c] * d0)
+    for r in range(t.n_rounds):
+        Rn, pn = [x.copy() for x in R], [x.copy() for x in p]
+        for c in range(dof):
+            src = (t.jump[c] >> (6 * r)) & 63
+            if src != 63:
+                Rn[c] = R[src] @ R[c]
+                pn[c] = R[src] @ p[c] + p[src]
+        R, p = Rn, pn
+    return np.array(R), np.array(p)
+
+
+@pytest.mark.parametrize("key", ALL_KEYS)
+def test_every_reference_config_compiles(key):
+    seq = build_product(key)
+    opt = seq.optimizer
+    t = opt.build_table()
+    assert t.magic == N.TABLE_MAGIC and t.nbytes == C.sizeof(N.DexrTable) == 8192
+    assert t.dof == opt.robot.dof and t.n_var == opt.opt_dof and t.n_fixed == len(opt.idx_pin2fixed)
+    # index maps: lane <-> target position
+    for k, lane in enumerate(opt.idx_pin2target):
+        assert t.var_index[lane] == k
+    for k, lane in enumerate(opt.idx_pin2fixed):
+        assert t.fixed_index[lane] == k
+    # bounds: limits widened by 1e-3 (optimizer.py:59-60), clip limits un-widened
+    for k, lane in enumerate(opt.idx_pin2target):
+        assert t.lower[lane] == pytest.approx(seq.joint_limits[k, 0] - 1e-3, abs=1e-6)
+        assert t.upper[lane] == pytest.approx(seq.joint_limits[k, 1] + 1e-3, abs=1e-6)
+        assert t.clip_lo[lane] == pytest.approx(seq.joint_limits[k, 0], abs=1e-6)
+    assert table_bytes(table_from_bytes(table_bytes(t))) == table_bytes(t)
+
+
+@pytest.mark.parametrize("key", ["teleop/allegro_hand_right", "offline/shadow_hand_right", "teleop/schunk_svh_hand_right",
+                                 "offline/schunk_svh_hand_left", "teleop/shadow_hand_left_dexpilot", "offline/panda_gripper",
+                                 "teleop/inspire_hand_right"])
+def test_table_fk_matches_model(key):
+    seq = build_product(key)
+    opt = seq.optimizer
+    t = opt.build_table()
+    kin = opt.robot.kin
+    rng = np.random.RandomState(2)
+    q = rng.uniform(kin.joint_limits[:, 0], kin.joint_limits[:, 1])
+    R, p = emulate_table_fk(t, q)
+    Rw, pw = kin.forward_kinematics(q)
+    np.testing.assert_allclose(R, Rw, atol=2e-6)  # table is float32
+    np.testing.assert_allclose(p, pw, atol=2e-6)
+    # link slots: parent lane + offset reproduce link positions; ancestor masks match the tree
+    anc = kin.is_ancestor_table()
+    spec = opt._objective_spec()
+    for k, name in enumerate(spec.link_names):
+        li = kin.link_index(name)
+        par = t.link_parent[k]
+        assert par == kin.link_parent[li]
+        pos = R[par] @ np.array(t.link_off[k][:]) + p[par] if par >= 0 else np.array(t.link_off[k][:])
+        np.testing.assert_allclose(pos, kin.link_pose(Rw, pw, li)[1], atol=3e-6)
+        mask = t.link_anc_mask[k]
+        for j in range(kin.dof):
+            assert bool((mask >> j) & 1) == (par >= 0 and bool(anc[par, j]))
+    for c in range(kin.dof):
+        for j in range(kin.dof):
+            assert bool((t.anc_mask[c] >> j) & 1) == bool(anc[c, j])
+            assert bool((t.desc_mask[c] >> j) & 1) == bool(anc[j, c])
+
+
+@pytest.mark.parametrize("key", ["teleop/schunk_svh_hand_right", "teleop/ability_hand_left", "offline/inspire_hand_right",
+                                 "teleop/panda_gripper"])
+def test_mimic_tables_match_adaptor(key):
+    seq = build_product(key)
+    opt = seq.optimizer
+    t = opt.build_table()
+    a = opt.adaptor
+    assert t.has_mimic == 1
+    o = build_oracle(key)
+    np.testing.assert_array_equal(a.idx_pin2mimic, o.adaptor.idx_pin2mimic)
+    np.testing.assert_array_equal(a.idx_pin2source, o.adaptor.idx_pin2source)
+    for i, lane in enumerate(a.idx_pin2mimic):
+        assert t.mimic_src[lane] == a.idx_pin2source[i]
+        assert t.mimic_mult[lane] == pytest.approx(a.multipliers[i])
+        assert t.mimic_off[lane] == pytest.approx(a.offsets[i])
+        assert t.var_index[lane] == -1 and t.fixed_index[lane] == -1
+    # groups: every variable lane lists itself first, then exactly its mimic joints
+    for lane in opt.idx_pin2target:
+        cnt = t.group_count[lane]
+        lanes = [t.group_lane[lane][f] for f in range(cnt)]
+        assert lanes[0] == lane and t.group_mult[lane][0] == 1.0
+        assert sorted(lanes[1:]) == sorted(int(m) for m, s in zip(a.idx_pin2mimic, a.idx_pin2source) if s == lane)
+    # host adaptor == oracle adaptor on qpos and Jacobian folding
+    rng = np.random.RandomState(0)
+    q = rng.randn(opt.robot.dof)
+    np.testing.assert_allclose(a.forward_qpos(q.copy()), o.adaptor.forward_qpos(q.copy()))
+    J = rng.randn(3, 3, opt.robot.dof)
+    np.testing.assert_allclose(a.backward_jacobian(J.copy()), o.adaptor.backward_jacobian(J.copy()))
+
+
+def test_objective_spec_indices():
+    seq = build_product("teleop/leap_hand_right_dexpilot")
+    opt = seq.optimizer
+    t = opt.build_table()
+    assert (t.loss, t.n_res, t.n_links, t.num_fingers, t.len_proj, t.len_s1) == (2, 10, 5, 4, 6, 3)
+    # default human indices = [origin, task] * 4 (optimizer.py:361-364)
+    assert [t.res_human_origin[k] for k in range(10)] == [8, 12, 16, 12, 16, 16, 0, 0, 0, 0]
+    assert [t.res_human_task[k] for k in range(10)] == [4, 4, 4, 8, 8, 12, 4, 8, 12, 16]
+    assert [t.s2_origin[k] for k in range(3)] == [1, 2, 2] and [t.s2_task[k] for k in range(3)] == [0, 0, 1]
+    seq = build_product("offline/shadow_hand_right")
+    t = seq.optimizer.build_table()
+    assert (t.loss, t.n_res, t.dof, t.n_var, t.n_rounds) == (0, 10, 30, 30, 4)
+    assert [t.res_human_task[k] for k in range(10)] == [4, 8, 12, 16, 20, 2, 6, 10, 14, 18]
+    assert all(t.res_origin[k] == -1 for k in range(10))
+
+
+def test_table_compiler_errors():
+    from dex_retargeting_b200.table import ObjectiveSpec, compile_table
+
+    seq = build_product("teleop/allegro_hand_right")
+    opt = seq.optimizer
+    kin = opt.robot.kin
+    spec = opt._objective_spec()
+    with pytest.raises(ValueError):
+        compile_table(kin, ["no_such_joint"], spec, np.zeros((1, 2)))
+    with pytest.raises(ValueError):
+        compile_table(kin, opt.target_joint_names, spec, np.zeros((3, 2)))
+    bad = ObjectiveSpec(spec.loss, spec.link_names, spec.res_task, spec.res_origin, [25] * 4, spec.res_human_origin)
+    with pytest.raises(ValueError):
+        compile_table(kin, opt.target_joint_names, bad, seq.joint_limits)
