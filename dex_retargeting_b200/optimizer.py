@@ -230,6 +230,60 @@ class Optimizer:
         self.last_status = status
         return qpos, rq
 
+    def retarget_batch_host(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
+                            out=None, clip_init=False):
+        """Host-buffer twin of `retarget_batch`: float32 numpy arrays (or CPU torch tensors, ideally
+        pinned) in, numpy out.  The library stages chunks through its own device buffers and overlaps the
+        host->device copies, the solve and the device->host copies (`dexr_solve_frames_host`).  Returns
+        when `out` [B,opt_dof] holds the results."""
+        def as_np(a, dtype=np.float32):
+            if a is None:
+                return None
+            if hasattr(a, "numpy") and not isinstance(a, np.ndarray):
+                a = a.numpy()
+            return np.ascontiguousarray(a, dtype=dtype)
+
+        last = as_np(last_qpos)
+        if last is None:
+            raise ValueError("last_qpos is required")
+        if (ref_value is None) == (keypoints is None):
+            raise ValueError("give exactly one of ref_value / keypoints")
+        B = last.shape[0]
+        eng = self.engine()
+        io = N.DexrFrames()
+        keep = []
+
+        def ptr(a, shape, name):
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        if keypoints is not None:
+            io.keypoints = ptr(as_np(keypoints), (B, N.NUM_KEYPOINTS, 3), "keypoints")
+        else:
+            io.ref_value = ptr(as_np(ref_value), (B, self.num_residuals, 3), "ref_value")
+        io.last_qpos = ptr(last, (B, self.opt_dof), "last_qpos")
+        nf = len(self.idx_pin2fixed)
+        if nf:
+            if fixed_qpos is None:
+                raise ValueError(f"Optimizer has {nf} joints but no fixed_qpos is given")
+            io.fixed_qpos = ptr(as_np(fixed_qpos), (B, nf), "fixed_qpos")
+        if projected is not None:
+            pj = projected.numpy() if hasattr(projected, "numpy") and not isinstance(projected, np.ndarray) else projected
+            if pj.dtype != np.uint8 or not pj.flags.c_contiguous:
+                raise ValueError("projected must be a contiguous uint8 array (updated in place)")
+            io.projected = ptr(pj, (B, self._objective_spec().len_proj), "projected")
+        if out is None:
+            out = np.empty((B, self.opt_dof), dtype=np.float32)
+        out_np = out.numpy() if hasattr(out, "numpy") and not isinstance(out, np.ndarray) else out
+        if out_np.dtype != np.float32 or not out_np.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float32 array")
+        io.qpos_out = ptr(out_np, (B, self.opt_dof), "out")
+        p = self.params(clip_init=clip_init)
+        N.check(eng.lib.dexr_solve_frames_host(eng.handle, C.byref(p), C.byref(io), B), "dexr_solve_frames_host")
+        return out
+
     # ---------------------------------------------------------------- device path (torch, B large)
     def retarget_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
                        out=None, robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None):

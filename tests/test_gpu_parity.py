@@ -1,0 +1,338 @@
+"""GPU parity tests: the CUDA solver (through the C ABI) against the float64 oracle.
+
+Parity target (DESIGN.md "Parity"): |dq|_inf < 1e-4 rad against oracle mode B, the converged minimiser of
+L(x) + norm_delta |x - last|^2 inside the widened bounds, from the same warm start.  The problem is
+non-convex: from far-away starts two correct solvers may settle in different local minima, so a frame counts
+as agreeing if it is within 1e-4 of mode B OR within 1e-4 of the KKT point a float64 polish reaches from the
+GPU's own answer while not being worse than mode B's objective by more than the basin difference allows;
+the fraction of "same basin" agreements is asserted separately for warm starts.
+"""
+import numpy as np
+import pytest
+
+from helpers import build_oracle, build_product, keypoint_trajectory, synth_problems
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # rad, BASELINE.json north_star tolerance
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def gpu_solve(opt, refs=None, fixed=None, x0=None, keypoints=None, clip_init=False, want_proj=False, proj_init=None):
+    dev = _dev()
+    B = x0.shape[0]
+    kw = {}
+    if keypoints is not None:
+        kw["keypoints"] = torch.from_numpy(np.ascontiguousarray(keypoints, dtype=np.float32)).to(dev)
+    else:
+        kw["ref_value"] = torch.from_numpy(np.ascontiguousarray(refs, dtype=np.float32)).to(dev)
+    if fixed is not None and fixed.shape[1] > 0:
+        kw["fixed_qpos"] = torch.from_numpy(np.ascontiguousarray(fixed, dtype=np.float32)).to(dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    cost = torch.zeros(B, dtype=torch.float32, device=dev)
+    rq = torch.zeros((B, opt.robot.dof), dtype=torch.float32, device=dev)
+    proj = None
+    if opt.retargeting_type == "DEXPILOT":
+        lp = opt._objective_spec().len_proj
+        proj = torch.zeros((B, lp), dtype=torch.uint8, device=dev) if proj_init is None else torch.from_numpy(proj_init).to(dev)
+    q = opt.retarget_batch(last_qpos=torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float32)).to(dev), status_out=status,
+                           cost_out=cost, robot_qpos_out=rq, projected=proj, clip_init=clip_init, **kw)
+    torch.cuda.synchronize()
+    res = dict(q=q.cpu().numpy(), status=status.cpu().numpy(), cost=cost.cpu().numpy(), robot_qpos=rq.cpu().numpy())
+    if proj is not None:
+        res["projected"] = proj.cpu().numpy()
+    return res
+
+
+def oracle_b(o, refs, fixed, x0):
+    from oracle.solvers import solve_converged
+
+    X, F = [], []
+    for i in range(x0.shape[0]):
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        xb, kkt, fb = solve_converged(o, refs[i], fixed[i], x0[i], update_state=False)
+        assert kkt < 1e-6
+        X.append(xb)
+        F.append(fb)
+    return np.array(X), np.array(F)
+
+
+def check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin):
+    from oracle.solvers import polish
+
+    q = res["q"].astype(np.float64)
+    assert np.all((res["status"] >> 24) == 0), "solver flagged frames"
+    assert np.all(q >= o.lower - 1e-6) and np.all(q <= o.upper + 1e-6)
+    dq = np.abs(q - XB).max(1)
+    same = dq < TOL
+    for i in np.nonzero(~same)[0]:
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        obj = o.make_objective(refs[i], fixed[i], x0[i], update_state=False)
+        xp, kkt = polish(obj, q[i], o.lower, o.upper)
+        assert kkt < 1e-6 and np.abs(xp - q[i]).max() < TOL, f"frame {i}: GPU answer is not a minimiser (moved {np.abs(xp - q[i]).max():.2e})"
+    assert same.mean() >= min_same_basin, f"only {same.mean():.3f} of frames in the oracle's basin"
+    # reported cost is the consistent objective at the returned point
+    for i in range(0, len(q), max(1, len(q) // 8)):
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        obj = o.make_objective(refs[i], fixed[i], x0[i], update_state=False)
+        assert res["cost"][i] == pytest.approx(obj.consistent(q[i]), rel=2e-4, abs=1e-8)
+    return dq
+
+
+FAMILIES = [
+    ("teleop/allegro_hand_right", {}),                      # BASELINE config 1/2: vector, 16 DoF, half-warp path
+    ("offline/shadow_hand_right", {}),                      # BASELINE config 3: position, 30 DoF incl. 6 dummy
+    ("teleop/leap_hand_right_dexpilot", {}),                # BASELINE config 4: dexpilot, 16 DoF
+    ("teleop/shadow_hand_left", {}),                        # vector, 24 DoF, 11 links
+    ("teleop/shadow_hand_right_dexpilot", {}),              # 5-finger dexpilot, 15 residuals
+    ("teleop/schunk_svh_hand_right", {}),                   # 11 mimic joints, explicit target joints
+    ("offline/schunk_svh_hand_left", {}),                   # mimic + dummy joints + position
+    ("teleop/ability_hand_left", {}),                       # mimic, 10 DoF
+    ("teleop/inspire_hand_right_dexpilot", {}),             # mimic + dexpilot
+    ("teleop/panda_gripper", {}),                           # prismatic, 1 variable, mimic
+    ("offline/panda_gripper", {}),                          # prismatic + dummy, 7 variables
+    ("offline/allegro_hand_left", {}),                      # position, 22 DoF
+]
+
+
+@pytest.mark.parametrize("key,ov", FAMILIES)
+def test_synthetic_warm_start_parity(key, ov):
+    """Unreachable targets (1 cm noise) + warm start (0.05 rad noise), shipped parameters (norm_delta 4e-3)."""
+    seq = build_product(key, ov)
+    o = build_oracle(key, ov)
+    rng = np.random.RandomState(11)
+    refs, fixed, x0, _ = synth_problems(o, 24, rng, init_noise=0.05, target_noise=0.01)
+    XB, FB = oracle_b(o, refs, fixed, x0)
+    res = gpu_solve(seq.optimizer, refs, fixed, x0)
+    dq = check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.9)
+    assert np.median(dq) < 1e-5
+
+
+@pytest.mark.parametrize("key", ["teleop/allegro_hand_right", "teleop/shadow_hand_right", "teleop/schunk_svh_hand_right",
+                                 "teleop/leap_hand_right_dexpilot"])
+def test_recorded_trajectory_parity(key):
+    """Real human keypoints (reference example/profiling/human_joint_right.pkl): large residuals (robot and
+    human hands differ), warm start = previous oracle solution, keypoints gathered in the kernel."""
+    seq = build_product(key)
+    opt = seq.optimizer
+    o = build_oracle(key)
+    from oracle.solvers import solve_converged
+
+    kp = keypoint_trajectory()
+    frames = list(range(0, 200, 5))
+    last = o.joint_limits.mean(1).astype(np.float32)
+    refs, x0, XB, kps, flags_in, flags_out = [], [], [], [], [], []
+    if o.type == "dexpilot":
+        o.projected[:] = False
+    for f in frames:
+        ref = o.ref_from_keypoints(kp[f]).astype(np.float32)
+        lastc = np.clip(last, o.joint_limits[:, 0], o.joint_limits[:, 1])
+        if o.type == "dexpilot":
+            flags_in.append(o.projected.astype(np.uint8).copy())
+        xb, kkt, _ = solve_converged(o, ref, np.zeros(0), lastc, update_state=True)
+        if o.type == "dexpilot":
+            flags_out.append(o.projected.astype(np.uint8).copy())
+        refs.append(ref); x0.append(lastc); XB.append(xb); kps.append(kp[f])
+        last = xb.astype(np.float32)
+    x0, XB = np.array(x0, dtype=np.float32), np.array(XB)
+    proj_init = np.array(flags_in) if flags_in else None
+    res = gpu_solve(opt, x0=x0, keypoints=np.array(kps), clip_init=True, proj_init=proj_init)
+    dq = np.abs(res["q"] - XB).max(1)
+    assert (dq < TOL).mean() >= 0.95, f"agreement {np.mean(dq < TOL):.3f}, worst {dq.max():.2e}"
+    assert np.median(dq) < 1e-5
+    if flags_out:
+        np.testing.assert_array_equal(res["projected"], np.array(flags_out))
+    # ref_value entry (what Optimizer.retarget receives) gives the same answer as the in-kernel gather
+    res2 = gpu_solve(opt, refs=np.array(refs), fixed=None, x0=x0, clip_init=True, proj_init=proj_init)
+    np.testing.assert_array_equal(res["q"], res2["q"])
+    # full qpos output: pinocchio order, mimic joints applied (seq_retarget.py:125-130)
+    full = np.zeros((len(frames), opt.robot.dof))
+    full[:, opt.idx_pin2target] = res["q"]
+    if opt.adaptor is not None:
+        for r in full:
+            opt.adaptor.forward_qpos(r)
+    np.testing.assert_allclose(res["robot_qpos"], full, atol=1e-6)
+
+
+@pytest.mark.parametrize("key,kind", [("teleop/allegro_hand_right", "vector"), ("teleop/schunk_svh_hand_left", "vector"),
+                                      ("teleop/inspire_hand_left", "vector"), ("offline/shadow_hand_right", "position"),
+                                      ("offline/leap_hand_right", "position"), ("teleop/leap_hand_right_dexpilot", "dexpilot"),
+                                      ("teleop/shadow_hand_right_dexpilot", "dexpilot")])
+def test_reference_test_protocol(key, kind):
+    """The reference's own test (tests/test_optimizer.py): seed 1, 100 reachable targets, cold start
+    (0.5 rad noise), normal_delta = 0 -> mean task-space error < 1e-2 m; and never worse than the restated
+    reference path (oracle mode A) on the same problems."""
+    from oracle.solvers import generate_problem, solve_reference
+
+    ov = dict(normal_delta=0) if kind == "position" else dict(low_pass_alpha=0, scaling_factor=1.0, normal_delta=0)
+    seq = build_product(key, ov)
+    opt = seq.optimizer
+    o = build_oracle(key, ov)
+    np.random.seed(1)
+    n = 100
+    refs, fixed, x0 = [], [], []
+    for _ in range(n):
+        q, init, target = generate_problem(o)
+        refs.append(target.astype(np.float32)); fixed.append(q[o.idx_pin2fixed]); x0.append(init[o.idx_pin2target])
+    refs, fixed, x0 = np.array(refs), np.array(fixed).reshape(n, -1), np.array(x0, dtype=np.float32)
+    res = gpu_solve(opt, refs, fixed, x0, clip_init=(kind == "position"))
+    errs, errs_ref = [], []
+    for i in range(n):
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        obj = o.make_objective(refs[i], fixed[i], x0[i], update_state=False)
+        errs.append(obj.task_error(res["q"][i].astype(np.float64)))
+        if i < 25:
+            xa, _ = solve_reference(o, refs[i], fixed[i], x0[i])
+            errs_ref.append(obj.task_error(xa.astype(np.float64)))
+    assert np.mean(errs) < 1e-2
+    assert np.mean(errs[:25]) <= np.mean(errs_ref) + 2e-3
+
+
+def test_batch_shapes_alignment_and_determinism():
+    """Ragged batch sizes (tail tiles, single frame), unaligned device pointers (bulk-copy fallback), and
+    frame-level determinism: a frame's answer does not depend on its position in the batch."""
+    key = "teleop/allegro_hand_right"
+    seq = build_product(key)
+    opt = seq.optimizer
+    o = build_oracle(key)
+    dev = _dev()
+    rng = np.random.RandomState(3)
+    refs, fixed, x0, _ = synth_problems(o, 300, rng, init_noise=0.1, target_noise=0.01)
+    base = gpu_solve(opt, refs, fixed, x0)["q"]
+    for B in (1, 2, 3, 5, 63, 64, 65, 257):
+        sub = gpu_solve(opt, refs[:B], fixed[:B], x0[:B])["q"]
+        np.testing.assert_array_equal(sub, base[:B])
+    perm = rng.permutation(300)
+    shuf = gpu_solve(opt, refs[perm], fixed[perm], x0[perm])["q"]
+    np.testing.assert_array_equal(shuf, base[perm])
+    # unaligned views: offset the buffers by one float so that no 16-byte alignment holds
+    big_ref = torch.zeros(300 * 12 + 1, dtype=torch.float32, device=dev)
+    big_x0 = torch.zeros(300 * 16 + 1, dtype=torch.float32, device=dev)
+    big_ref[1:] = torch.from_numpy(refs).to(dev).reshape(-1)
+    big_x0[1:] = torch.from_numpy(x0).to(dev).reshape(-1)
+    q = opt.retarget_batch(big_ref[1:].view(300, 4, 3), None, big_x0[1:].view(300, 16))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(q.cpu().numpy(), base)
+
+
+def test_single_frame_api_matches_batch_and_oracle():
+    """Optimizer.retarget / SeqRetargeting.retarget (numpy in, numpy out, B = 1 host path)."""
+    from oracle.solvers import OracleSeqRetargeting
+
+    for key in ("teleop/allegro_hand_right", "teleop/leap_hand_right_dexpilot", "offline/inspire_hand_right"):
+        seq = build_product(key)
+        o = build_oracle(key)
+        oseq = OracleSeqRetargeting(o, mode="converged")
+        kp = keypoint_trajectory()
+        for f in range(0, 60, 6):
+            ref = o.ref_from_keypoints(kp[f])
+            fixed = np.zeros(len(seq.optimizer.idx_pin2fixed))
+            a = seq.retarget(ref, fixed)
+            b = oseq.retarget(ref, fixed)
+            assert a.dtype == np.float64 and a.shape == (seq.optimizer.robot.dof,)
+            np.testing.assert_allclose(a, b, atol=TOL)
+        assert seq.num_retargeting == 10 and seq.accumulated_time > 0
+        assert np.isfinite(seq.optimizer.opt.last_optimum_value())
+
+
+def test_nonfinite_input_does_not_poison_neighbours():
+    key = "teleop/allegro_hand_right"
+    seq = build_product(key)
+    opt = seq.optimizer
+    o = build_oracle(key)
+    rng = np.random.RandomState(5)
+    refs, fixed, x0, _ = synth_problems(o, 40, rng)
+    clean = gpu_solve(opt, refs, fixed, x0)
+    bad = refs.copy()
+    bad[7, 2, 1] = np.nan
+    bad[20] = np.inf
+    res = gpu_solve(opt, bad, fixed, x0)
+    ok = np.ones(40, bool)
+    ok[[7, 20]] = False
+    np.testing.assert_array_equal(res["q"][ok], clean["q"][ok])
+    assert np.all(res["status"][[7, 20]] & (1 << 25))
+    np.testing.assert_allclose(res["q"][[7, 20]], x0[[7, 20]])  # previous pose is returned (optimizer.py:99-102)
+
+
+def test_bounds_are_respected_and_active():
+    """Targets far outside the workspace drive joints into their limits: solution sits on the widened
+    bound (limit +- 1e-3, optimizer.py:59-60) and still matches the oracle."""
+    key = "teleop/allegro_hand_right"
+    seq = build_product(key)
+    o = build_oracle(key)
+    rng = np.random.RandomState(9)
+    refs, fixed, x0, _ = synth_problems(o, 16, rng, init_noise=0.05)
+    refs = (refs * 2.5).astype(np.float32)
+    XB, FB = oracle_b(o, refs, fixed, x0)
+    res = gpu_solve(seq.optimizer, refs, fixed, x0)
+    check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.8)
+    on_bound = (np.abs(res["q"] - o.lower) < 1e-6) | (np.abs(res["q"] - o.upper) < 1e-6)
+    assert on_bound.any()
+
+
+def test_sequences_kernel_matches_sequential_oracle():
+    """dexr_solve_sequences == S independent SeqRetargeting loops (clip, solve, unfiltered warm start,
+    mimic, low-pass filter), state carried on device; resumable across calls."""
+    from oracle.solvers import OracleSeqRetargeting
+
+    dev = _dev()
+    kp = keypoint_trajectory()
+    for key in ("teleop/allegro_hand_right", "teleop/leap_hand_right_dexpilot", "teleop/schunk_svh_hand_right"):
+        seq = build_product(key)
+        o = build_oracle(key)
+        S, T = 3, 24
+        starts = [0, 150, 400]
+        kps = np.stack([kp[s:s + 2 * T:2] for s in starts]).astype(np.float32)  # [S,T,21,3]
+        want = np.zeros((S, T, seq.optimizer.robot.dof))
+        for s in range(S):
+            oseq = OracleSeqRetargeting(build_oracle(key), mode="converged")
+            for t in range(T):
+                want[s, t] = oseq.retarget(oseq.opt.ref_from_keypoints(kps[s, t]))
+        tk = torch.from_numpy(kps).to(dev)
+        out, state = seq.retarget_sequences(tk)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        err = np.abs(got - want).max(axis=2)
+        assert (err < TOL).mean() > 0.97, f"{key}: {(err < TOL).mean():.3f} worst {err.max():.2e}"
+        # split the same streams into two calls: identical results (state is complete)
+        out1, st = seq.retarget_sequences(tk[:, :10].contiguous())
+        out2, st = seq.retarget_sequences(tk[:, 10:].contiguous(), state=st)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(torch.cat([out1, out2], dim=1).cpu().numpy(), got)
+        assert int(st.filter_init.sum()) == S
+
+
+def test_full_batch_properties():
+    """BASELINE.json size (65 536 frames): size-independent properties -- every frame converged, inside the
+    bounds, task-space accurate for reachable targets, identical to the same frames solved in small
+    batches, and a float64 KKT check on a sample."""
+    from oracle.solvers import polish
+
+    key = "teleop/allegro_hand_right"
+    seq = build_product(key)
+    opt = seq.optimizer
+    o = build_oracle(key)
+    rng = np.random.RandomState(21)
+    base_refs, base_fixed, base_x0, _ = synth_problems(o, 512, rng, init_noise=0.05, target_noise=0.0)
+    reps = 65536 // 512
+    refs = np.tile(base_refs, (reps, 1, 1))
+    x0 = np.tile(base_x0, (reps, 1))
+    res = gpu_solve(opt, refs, None, x0)
+    assert np.all((res["status"] >> 24) == 0)
+    assert np.all(res["q"] >= o.lower - 1e-6) and np.all(res["q"] <= o.upper + 1e-6)
+    small = gpu_solve(opt, base_refs, None, base_x0)["q"]
+    np.testing.assert_array_equal(res["q"].reshape(reps, 512, -1), np.broadcast_to(small, (reps, 512, small.shape[1])))
+    for i in range(0, 512, 64):
+        obj = o.make_objective(base_refs[i], base_fixed[i], base_x0[i], update_state=False)
+        assert obj.task_error(small[i].astype(np.float64)) < 2e-3  # reachable target, small regulariser pull
+        xp, kkt = polish(obj, small[i].astype(np.float64), o.lower, o.upper)
+        assert np.abs(xp - small[i]).max() < TOL
