@@ -181,6 +181,34 @@ class OracleRobot:
         return J
 
 
+    def link_position_hessian_contraction(self, link_ids, gpos):
+        """sum_l sum_c gpos[l,c] * d2 p_l[c] / dq_i dq_j  as a (dof, dof) matrix (float64, explicit loops).
+
+        Second derivatives of a point rigidly attached below joints i (closer to the root) and j:
+          i revolute, j revolute : a_i x (a_j x (p - o_j))
+          i revolute, j prismatic: a_i x a_j
+          i prismatic            : 0
+        (a = world axis, o = world joint origin).  Used by the oracle's Newton polish only."""
+        S = np.zeros((self.dof, self.dof))
+        for r, lid in enumerate(link_ids):
+            name = self.link_names[lid]
+            p = self._poses[name][:3, 3]
+            chain = self._chains[name]
+            g = gpos[r]
+            for u, ji in enumerate(chain):
+                ai, oi, ti, i = self._joint_frames[ji]
+                if ti != "revolute":
+                    continue
+                for jj in chain[u:]:
+                    aj, oj, tj, j = self._joint_frames[jj]
+                    d = np.cross(ai, np.cross(aj, p - oj)) if tj == "revolute" else np.cross(ai, aj)
+                    v = float(g @ d)
+                    S[i, j] += v
+                    if i != j:
+                        S[j, i] += v
+        return S
+
+
 class OracleMimic:
     """kinematics_adaptor.py:46-113."""
 

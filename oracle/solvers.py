@@ -48,9 +48,8 @@ def _consistent_value_and_grad(obj):
 
 
 def polish(obj, x, lo, hi, iters=200, tol=1e-13):
-    """Float64 projected Levenberg-Marquardt on F = L + norm_delta |x - x_last|^2 with a
-    finite-difference-free generalized Gauss-Newton model: H = sum_k J_k^T (d2 loss / d r_k^2) J_k
-    + 2 norm_delta I.  Used to drive a good iterate to a KKT point; returns (x, kkt residual)."""
+    """Float64 projected, damped Newton on F = L + norm_delta |x - x_last|^2 with the exact Hessian.
+    Used to drive a good iterate to a KKT point; returns (x, kkt residual)."""
     o = obj.o
     f = _consistent_value_and_grad(obj)
     x = np.clip(np.asarray(x, float), lo, hi)
@@ -63,9 +62,10 @@ def polish(obj, x, lo, hi, iters=200, tol=1e-13):
         free = ~(((x <= lo) & (g > 0)) | ((x >= hi) & (g < 0)))
         improved = False
         for _try in range(30):
-            A = H + lam * np.diag(np.diag(H))
+            A = H + lam * np.diag(np.abs(np.diag(H)) + 1e-9)
             A = A[np.ix_(free, free)]
             try:
+                np.linalg.cholesky(A)  # the exact Hessian can be indefinite away from a minimum
                 step = -np.linalg.solve(A, g[free])
             except np.linalg.LinAlgError:
                 lam *= 10
@@ -85,12 +85,27 @@ def polish(obj, x, lo, hi, iters=200, tol=1e-13):
     return x, projected_gradient_norm(x, g, lo, hi)
 
 
+def _fold(o, Hq):
+    """pinocchio-order (dof x dof) -> variable order (n x n): M^T Hq M with q = M x + c (mimic map)."""
+    M = np.zeros((o.robot.dof, o.opt_dof))
+    M[o.idx_pin2target, np.arange(o.opt_dof)] = 1.0
+    if o.adaptor is not None:
+        a = o.adaptor
+        for i in range(len(a.idx_pin2mimic)):
+            M[a.idx_pin2mimic[i], a.idx_target2source[i]] = a.multipliers[i]
+    return M.T @ Hq @ M
+
+
 def _ggn_hessian(obj, x):
+    """Exact Hessian of the consistent objective: loss curvature through the Jacobian + the kinematic
+    second-derivative term + the regulariser."""
     o = obj.o
     pos, J = obj._kin(x, True)
     n = o.opt_dof
     H = 2.0 * o.norm_delta * np.eye(n)
     beta = o.huber_delta
+    _, gpos = obj._loss(pos, True)
+    H += _fold(o, o.robot.link_position_hessian_contraction(o.link_ids, gpos))
     if o.type == "position":
         d = pos - obj.target
         w = np.where(np.abs(d) < beta, 1.0 / beta, 0.0) / d.size
@@ -119,7 +134,7 @@ def solve_converged(opt: OracleOptimizer, ref_value, fixed_qpos, last_qpos, x_in
     x0 = np.asarray(last_qpos if x_init is None else x_init, dtype=np.float64)
     x0 = np.clip(x0, opt.lower, opt.upper)
     res = minimize(f, x0, jac=True, method="SLSQP", bounds=list(zip(opt.lower, opt.upper)),
-                   options=dict(ftol=1e-15, maxiter=2000))
+                   options=dict(ftol=1e-9, maxiter=300))
     x, kkt = polish(obj, res.x, opt.lower, opt.upper)
     return x, kkt, obj.consistent(x)
 
