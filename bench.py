@@ -182,10 +182,18 @@ class CpuReferencePool:
 
 
 def host_cores():
+    """Usable host cores: scheduler affinity, capped by the cgroup CPU quota when there is one."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return max(1, os.cpu_count() or 1)
+        n = os.cpu_count() or 1
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
 
 
 # --------------------------------------------------------------------------------------- main
@@ -336,7 +344,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             cores = host_cores()
-            n_s = int(min(2048, max(64, cores * 24)))
+            n_s = int(min(16384, max(64, cores * 64)))
             pool = CpuReferencePool(cores, kp_h, x0_h)
             r = pool.frames_per_second(kp_h[:n_s], x0_h[:n_s])
             pool.close()

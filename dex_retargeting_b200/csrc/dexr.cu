@@ -336,7 +336,7 @@ void dexr_default_params(dexr_params_t* p) {
   p->eta2 = 3e-2f;
   p->lp_alpha = -1.0f;
   p->tol = 1e-5f;
-  p->lambda0 = 1e-3f;
+  p->lambda0 = 1e-2f;
   p->max_iters = 64;
   p->clip_init = 0;
 }

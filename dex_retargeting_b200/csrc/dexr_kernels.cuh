@@ -35,6 +35,8 @@ constexpr float kNoise = 2e-6f;      // relative fp32 noise floor of the objecti
 constexpr float kLamMin = 1e-7f;
 constexpr float kLamDown = 0.1f;
 constexpr float kLamUp = 10.0f;
+constexpr float kNearStep = 0.1f;    // accepted step (rad / m) below which the exact radial loss curvature is used
+constexpr float kFarResidual = 0.2f; // residual (m) above which the kinematic curvature term is left out
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -418,6 +420,10 @@ struct Solver {
     float lam = prm.lambda0;
     int iters = 0, rejects = 0;
     bool done = !active;
+    // Curvature model (group-uniform): `exact` = use the true second derivative of the norm-Huber loss
+    // (radial direction has zero curvature beyond beta); otherwise its quadratic majoriser 1/d * I, which
+    // is positive semi-definite and globally safer.  Optimistic start, demoted after a large or failed step.
+    bool exact = true;
 
     while (gany<32>(!done, lane)) {
       // ======================= gradient + exact Hessian at x ===========================
@@ -432,6 +438,7 @@ struct Solver {
       const int m = st->n_res;
       const int loss = st->loss;
       const float4* lpc = lp(cur);
+      float rmax = 0.f;
       for (int k = 0; k < m; ++k) {
         const int ti = st->res_task[k], oi = st->res_origin[k];
         const float4 T = fr()[k];
@@ -460,22 +467,23 @@ struct Solver {
         // loss derivatives wrt the residual block (uniform across lanes)
         float gx, gy, gz, y0, y1, y2;
         if (loss == DEXR_LOSS_POSITION) {
-          const bool qx = fabsf(rx) < beta, qy = fabsf(ry) < beta, qz = fabsf(rz) < beta;
-          gx = T.w * (qx ? rx * inv_beta : copysignf(1.f, rx));
-          gy = T.w * (qy ? ry * inv_beta : copysignf(1.f, ry));
-          gz = T.w * (qz ? rz * inv_beta : copysignf(1.f, rz));
-          y0 = qx ? T.w * inv_beta * j0 : 0.f;
-          y1 = qy ? T.w * inv_beta * j1 : 0.f;
-          y2 = qz ? T.w * inv_beta * j2 : 0.f;
+          // per-coordinate Huber: exact curvature is 0 beyond beta; the majoriser 1/max(|r|, beta) is
+          // used throughout (identical inside the quadratic zone)
+          const float ax_ = fabsf(rx), ay_ = fabsf(ry), az_ = fabsf(rz);
+          rmax = fmaxf(rmax, fmaxf(ax_, fmaxf(ay_, az_)));
+          const float wx = 1.0f / fmaxf(ax_, beta), wy = 1.0f / fmaxf(ay_, beta), wz = 1.0f / fmaxf(az_, beta);
+          gx = T.w * rx * wx; gy = T.w * ry * wy; gz = T.w * rz * wz;
+          y0 = T.w * wx * j0; y1 = T.w * wy * j1; y2 = T.w * wz * j2;
         } else {
           const float d = sqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
+          rmax = fmaxf(rmax, d);
           const bool quad = d < beta;
           const float invd = d > 0.f ? 1.0f / d : 0.f;
           const float ux = rx * invd, uy = ry * invd, uz = rz * invd;
           const float hp = quad ? d * inv_beta : 1.0f;
           gx = T.w * hp * ux; gy = T.w * hp * uy; gz = T.w * hp * uz;
           const float s_iso = T.w * (quad ? inv_beta : invd);
-          const float s_rad = quad ? 0.f : T.w * invd;
+          const float s_rad = (quad || !exact) ? 0.f : T.w * invd;
           const float uj = s_rad * fmaf(ux, j0, fmaf(uy, j1, uz * j2));
           y0 = fmaf(s_iso, j0, -uj * ux); y1 = fmaf(s_iso, j1, -uj * uy); y2 = fmaf(s_iso, j2, -uj * uz);
         }
@@ -501,6 +509,7 @@ struct Solver {
       // ---- FK curvature: S[i][c] = a_i . t_c (i ancestor-or-self of c), symmetric otherwise ----
       {
         const float ar0 = rev ? a[0] : 0.f, ar1 = rev ? a[1] : 0.f, ar2 = rev ? a[2] : 0.f;
+        const bool curv_on = rmax < kFarResidual;  // far from the targets the term is large and indefinite
         at()[2 * l] = make_float4(ar0, ar1, ar2, 0.f);
         at()[2 * l + 1] = make_float4(t0, t1, t2, 0.f);
         __syncwarp();
@@ -513,7 +522,7 @@ struct Solver {
             const bool dn = (desc >> i) & 1u;
             const float vu = fmaf(ai.x, t0, fmaf(ai.y, t1, ai.z * t2));
             const float vd = fmaf(ar0, ti_.x, fmaf(ar1, ti_.y, ar2 * ti_.z));
-            H[i] += up ? vu : (dn ? vd : 0.f);
+            H[i] += curv_on ? (up ? vu : (dn ? vd : 0.f)) : 0.f;
           }
         }
       }
@@ -580,6 +589,7 @@ struct Solver {
       }
       // ======================= damped Newton trials ====================================
       bool accepted = done;
+      float acc_step = 0.f;
       float Rn[9], pn[3];
       for (int trial = 0; trial < kMaxTrials; ++trial) {
         if (!gany<32>(!accepted, lane)) break;
@@ -652,6 +662,7 @@ struct Solver {
             cur ^= 1;
             lam = fmaxf(lam * kLamDown, kLamMin);
             accepted = true;
+            acc_step = step;
             if (step < prm.tol) done = true;
           } else {
             lam *= kLamUp;
@@ -661,7 +672,11 @@ struct Solver {
         __syncwarp();
       }
       if (!done) {
-        if (!accepted) done = true;  // no descent direction left at fp32 resolution
+        if (!accepted) {
+          if (exact) lam = prm.lambda0;  // retry this point with the majoriser model
+          else done = true;              // no descent direction left at fp32 resolution
+        }
+        exact = accepted && acc_step < kNearStep;
         ++iters;
         if (iters >= prm.max_iters && !done) { done = true; status |= DEXR_STATUS_MAXITER; }
       }

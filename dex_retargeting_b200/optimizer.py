@@ -104,7 +104,7 @@ class Optimizer:
         # solver knobs that have no counterpart in the reference
         self.max_iters = 64
         self.step_tol = 1e-5
-        self.lambda0 = 1e-3
+        self.lambda0 = 1e-2
 
     # ---------------------------------------------------------------- reference API
     def set_joint_limit(self, joint_limits: np.ndarray, epsilon=1e-3):

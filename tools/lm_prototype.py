@@ -106,6 +106,9 @@ class ProtoProblem:
 
 
 NOISE = 2e-6
+RFAR = 0.2
+LDOWN = 0.1
+LUP = 10.0
 STATS = {'solves': 0}
 
 
@@ -114,7 +117,7 @@ def huber(d, beta):
 
 
 def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, tol=1e-6, ggn=True, lam0=1e-3,
-                verbose=False, newton=False):
+                verbose=False, newton=False, hybrid=False, near=0.1, curv_far=True, pos_majorise=False, start_exact=False):
     """target [B,m,3] (already scaled / projected), weights [B,m] or None (position)."""
     o, dt = P.o, P.dt
     B, n = x0.shape
@@ -140,12 +143,14 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
         return L + nd * ((x - last) ** 2).sum(1)
 
     lam = np.full(B, lam0, dt)
+    exact = (np.ones(B, bool) if start_exact else np.zeros(B, bool)) if hybrid else np.full(B, ggn)
     done = np.zeros(B, bool)
     iters = np.zeros(B, int)
     pos, J = P.fk(x, fixed)
     r = residuals(pos)
     F = cost(r, x)
     for it in range(max_iter):
+        x_prev = x.copy()
         # gradient / GGN Hessian at x
         if o.type == "position":
             Jr = J.reshape(B, -1, n)
@@ -153,7 +158,8 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             quad = np.abs(rr) < beta
             c = dt(1.0 / rr.shape[1])
             gres = np.where(quad, rr / beta, np.sign(rr)) * c
-            wrow = np.where(quad, 1 / beta, 0.0) * c
+            ex_pos = exact & (not pos_majorise)
+            wrow = np.where(ex_pos[:, None], np.where(quad, 1 / beta, 0.0), 1.0 / np.maximum(np.abs(rr), beta)) * c
             g = np.einsum("br,brn->bn", gres, Jr)
             H = np.einsum("br,bri,brj->bij", wrow, Jr, Jr)
         else:
@@ -167,10 +173,9 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             g = np.einsum("bk,bkc,bkcn->bn", ck * hp, u, Jv)
             a_iso = np.where(quad, 1 / beta, 1 / dsafe) * ck
             H = np.einsum("bk,bkci,bkcj->bij", a_iso, Jv, Jv)
-            if ggn:
-                uJ = np.einsum("bkc,bkcn->bkn", u, Jv)
-                a_rad = np.where(quad, 0.0, 1 / dsafe) * ck
-                H -= np.einsum("bk,bki,bkj->bij", a_rad, uJ, uJ)
+            uJ = np.einsum("bkc,bkcn->bkn", u, Jv)
+            a_rad = np.where(quad, 0.0, 1 / dsafe) * ck * exact[:, None]
+            H -= np.einsum("bk,bki,bkj->bij", a_rad, uJ, uJ)
         if newton:
             if o.type == "position":
                 gpos = gres.reshape(r.shape)
@@ -180,7 +185,9 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
                 for k in range(o.m):
                     gpos[:, o.task_sel[k]] += gv[:, k]
                     gpos[:, o.origin_sel[k]] -= gv[:, k]
-            H = H + P.curvature(gpos)
+            rmax = np.abs(r).reshape(B, -1).max(1) if o.type == 'position' else np.linalg.norm(r, axis=2).max(1)
+            cw = np.ones(B, dt) if (curv_far or not hybrid) else (rmax < RFAR).astype(dt)
+            H = H + P.curvature(gpos) * cw[:, None, None]
         g = g + 2 * nd * (x - last)
         H = H + 2 * nd * np.eye(n, dtype=dt)[None]
         act = ((x <= lo) & (g > 0)) | ((x >= hi) & (g < 0))
@@ -190,11 +197,15 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
         diag = np.abs(H_f[:, np.arange(n), np.arange(n)]) + dt(1e-6)
         # inner loop: try lambdas
         accepted = done.copy()
+        switch = np.zeros(B, bool)
         for trial in range(8):
             STATS['solves'] += int((~accepted).sum())
             A = H_f.copy()
             A[:, np.arange(n), np.arange(n)] += lam[:, None] * diag
             pd = np.linalg.eigvalsh(A.astype(np.float64)).min(1) > 0
+            if False and hybrid and start_exact and trial == 0:
+                switch = exact & ~pd & ~accepted
+                accepted = accepted | switch
             A[~pd] = np.eye(n, dtype=dt)
             delta = -np.linalg.solve(A.astype(np.float64), g_f.astype(np.float64)[..., None])[..., 0].astype(dt)
             delta[~pd] = 0
@@ -215,12 +226,19 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             newly_done = upd & (step < tol)
             iters += (~done).astype(int) * (0 if trial else 1)
             done |= newly_done
-            lam = np.where(upd, np.maximum(lam * dt(0.1), dt(1e-7)), np.where(accepted, lam, lam * dt(10)))
+            lam = np.where(upd, np.maximum(lam * dt(LDOWN), dt(1e-7)), np.where(accepted, lam, lam * dt(LUP)))
             accepted |= upd
             if accepted.all():
                 break
         stuck = ~accepted
-        done |= stuck  # could not improve: at (numerical) minimum
+        if hybrid:
+            done |= stuck & ~exact  # the majoriser model failed too: at the (numerical) minimum
+            laststep = np.abs(x - x_prev).max(1)
+            exact = (~stuck) & (laststep < near) & ~switch
+            if start_exact:
+                lam = np.where(switch, dt(lam0), lam)
+        else:
+            done |= stuck  # could not improve: at (numerical) minimum
         if verbose:
             print(it, "active", (~done).sum(), "F mean", F.mean())
         if done.all():
