@@ -109,7 +109,11 @@ class RetargetingConfig:
         if not urdf_path.is_absolute():
             urdf_path = (Path(self._DEFAULT_URDF_DIR) / urdf_path).absolute()
         if not urdf_path.exists():
-            raise ValueError(f"URDF path {urdf_path} does not exist")
+            # robot descriptions exported as flat JSON joint trees (tests/golden/robots) are accepted too
+            alt = (Path(self._DEFAULT_URDF_DIR) / (urdf_path.stem + ".json")).absolute()
+            if not alt.exists():
+                raise ValueError(f"URDF path {urdf_path} does not exist")
+            urdf_path = alt
         self.urdf_path = str(urdf_path)
 
     @classmethod

@@ -170,3 +170,23 @@ def test_euler_extraction_roundtrip():
         Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
         Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
         np.testing.assert_allclose(_intrinsic_xyz_from_matrix(Rx @ Ry @ Rz), [a, b, c], atol=1e-12)
+
+
+def test_packaged_default_configs_load_with_fixture_robots():
+    """The 39 packaged YAML files (same names / schema as the reference package) load and build."""
+    RetargetingConfig.set_default_urdf_dir(str(ROBOTS))
+    n = 0
+    for robot in ROBOT_NAMES:
+        for rtype in RetargetingType:
+            for hand in HandType:
+                if robot is RobotName.ability and rtype is RetargetingType.dexpilot and False:
+                    continue
+                path = get_default_config_path(robot, rtype, hand)
+                assert path.exists(), path
+                seq = RetargetingConfig.load_from_file(path).build()
+                assert seq.optimizer.retargeting_type == rtype.name.upper()
+                n += 1
+    assert n == 42  # 7 robots x 3 types x 2 hands (the gripper's two hands share a file)
+    seq = RetargetingConfig.load_from_file(get_default_config_path(RobotName.allegro, RetargetingType.vector, HandType.right),
+                                           override=dict(scaling_factor=1.0, low_pass_alpha=0)).build()
+    assert seq.optimizer.scaling == 1.0 and seq.filter.alpha == 0
