@@ -424,6 +424,10 @@ struct Solver {
     // (radial direction has zero curvature beyond beta); otherwise its quadratic majoriser 1/d * I, which
     // is positive semi-definite and globally safer.  Optimistic start, demoted after a large or failed step.
     bool exact = true;
+    // A tiny accepted step ends the frame -- unless some variable is held at a bound: then the gradient is
+    // re-evaluated once more, and the frame ends only if the same set stays active (KKT on the bounds).
+    bool recheck = false;
+    unsigned last_fmask = 0u;
 
     while (gany<32>(!done, lane)) {
       // ======================= gradient + exact Hessian at x ===========================
@@ -572,6 +576,10 @@ struct Solver {
       const bool act = isvar && ((x <= lo && g > 0.f) || (x >= hi && g < 0.f));
       const bool free_ = isvar && !act;
       const unsigned fmask = gballot<G>(free_, lane);
+      const bool any_act = gany<G>(act, lane);
+      if (recheck && fmask == last_fmask) done = true;
+      recheck = false;
+      last_fmask = fmask;
       float hd = 1.0f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
@@ -663,7 +671,10 @@ struct Solver {
             lam = fmaxf(lam * kLamDown, kLamMin);
             accepted = true;
             acc_step = step;
-            if (step < prm.tol) done = true;
+            if (step < prm.tol) {
+              if (any_act) recheck = true;
+              else done = true;
+            }
           } else {
             lam *= kLamUp;
             ++rejects;
