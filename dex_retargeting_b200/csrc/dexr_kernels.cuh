@@ -35,6 +35,7 @@ constexpr float kNoise = 2e-6f;      // relative fp32 noise floor of the objecti
 constexpr float kLamMin = 1e-7f;
 constexpr float kLamDown = 0.1f;
 constexpr float kLamUp = 10.0f;
+constexpr float kGradNoise = 1e-7f;  // |dF/dx| below this is indistinguishable from 0 in fp32
 constexpr float kNearStep = 0.1f;    // accepted step (rad / m) below which the exact radial loss curvature is used
 constexpr float kFarResidual = 0.2f; // residual (m) above which the kinematic curvature term is left out
 
@@ -427,6 +428,7 @@ struct Solver {
     // A tiny accepted step ends the frame -- unless some variable is held at a bound: then the gradient is
     // re-evaluated once more, and the frame ends only if the same set stays active (KKT on the bounds).
     bool recheck = false;
+    int rechecks = 0;
     unsigned last_fmask = 0u;
 
     while (gany<32>(!done, lane)) {
@@ -573,11 +575,12 @@ struct Solver {
       // ---- regulariser, active set (box bounds), freeze ----
       const bool isvar = var >= 0;
       g = isvar ? fmaf(2.0f * nd, x - x0, g) : 0.f;
-      const bool act = isvar && ((x <= lo && g > 0.f) || (x >= hi && g < 0.f));
+      // a variable sitting on a bound stays active unless the gradient points inward by more than fp32 noise
+      const bool act = isvar && ((x <= lo && g > -kGradNoise) || (x >= hi && g < kGradNoise));
       const bool free_ = isvar && !act;
       const unsigned fmask = gballot<G>(free_, lane);
       const bool any_act = gany<G>(act, lane);
-      if (recheck && fmask == last_fmask) done = true;
+      if (recheck && (fmask == last_fmask || ++rechecks >= 3)) done = true;
       recheck = false;
       last_fmask = fmask;
       float hd = 1.0f;

