@@ -662,7 +662,11 @@ struct Solver {
         write_links(Rn, pn, cur ^ 1);
         __syncwarp();
         const float Fn = cost(cur ^ 1, xn);
-        const bool ok = !bad && isfinite(Fn) && (Fn <= F || step < prm.tol || pred < kNoise * fabsf(F));
+        const float fnoise = kNoise * fabsf(F);
+        const bool ok = !bad && isfinite(Fn) && (Fn <= F || step < prm.tol || pred < fnoise);
+        // the damping is relaxed only after a decrease that fp32 can actually resolve; steps accepted on
+        // trust (below the noise floor of F) keep it, so the iteration contracts instead of wandering
+        const bool verified = Fn < F - fnoise;
         if (!accepted) {
           if (ok) {
             x = xn; q = qn; F = Fn;
@@ -671,7 +675,7 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < 3; ++i) p[i] = pn[i];
             cur ^= 1;
-            lam = fmaxf(lam * kLamDown, kLamMin);
+            if (verified) lam = fmaxf(lam * kLamDown, kLamMin);
             accepted = true;
             acc_step = step;
             if (step < prm.tol) {

@@ -108,6 +108,7 @@ class ProtoProblem:
 NOISE = 2e-6
 RFAR = 0.2
 LDOWN = 0.1
+KEEP_LAM_ON_NOISE = True
 LUP = 10.0
 STATS = {'solves': 0}
 
@@ -217,6 +218,7 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             pred = 0.5 * ((xn - x) * (lam[:, None] * diag * (xn - x) - g_f)).sum(1)
             noise = dt(NOISE) * np.abs(F)
             ok = ((Fn <= F) | (step < tol) | (pred < noise)) & pd
+            F_before = F.copy()
             upd = ok & ~accepted
             x = np.where(upd[:, None], xn, x)
             pos = np.where(upd[:, None, None], posn, pos)
@@ -226,7 +228,8 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             newly_done = upd & (step < tol)
             iters += (~done).astype(int) * (0 if trial else 1)
             done |= newly_done
-            lam = np.where(upd, np.maximum(lam * dt(LDOWN), dt(1e-7)), np.where(accepted, lam, lam * dt(LUP)))
+            verified = Fn < F_before - noise if KEEP_LAM_ON_NOISE else np.ones(B, bool)
+            lam = np.where(upd & verified, np.maximum(lam * dt(LDOWN), dt(1e-7)), np.where(accepted | upd, lam, lam * dt(LUP)))
             accepted |= upd
             if accepted.all():
                 break
