@@ -27,7 +27,7 @@ struct FrameArgs {
   int ntiles;
   int use_bulk;   // inputs 16-byte aligned -> cp.async.bulk for full tiles
   int in_row;     // floats per frame of the kp/ref input (63 or 3m)
-  int n_var, n_fixed, dof, len_proj;
+  Dims dm;
   int off_in, off_last, off_fixed, stage_bytes;  // ring stage layout (bytes)
   int ring_off, bar_off, scratch_off;            // dynamic smem layout (bytes)
 };
@@ -38,7 +38,7 @@ struct SeqArgs {
   dexr_sequences_t io;
   long long S;
   int steps;
-  int n_var, n_fixed, dof, len_proj;
+  Dims dm;
   int scratch_off;
 };
 
@@ -85,14 +85,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
       float* s_last = reinterpret_cast<float*>(sb + a.off_last);
       float* s_fixed = reinterpret_cast<float*>(sb + a.off_fixed);
       const float* gi = g_in + f0 * a.in_row;
-      const float* gl = a.io.last_qpos + f0 * a.n_var;
-      const float* gf = a.n_fixed > 0 ? a.io.fixed_qpos + f0 * a.n_fixed : nullptr;
+      const float* gl = a.io.last_qpos + f0 * a.dm.n_var;
+      const float* gf = a.dm.n_fixed > 0 ? a.io.fixed_qpos + f0 * a.dm.n_fixed : nullptr;
       if (lane == 0) next[stage] = 0;
       if (a.use_bulk && (count & 3) == 0) {
         if (lane == 0) {
           const uint32_t b_in = (uint32_t)count * a.in_row * 4u;
-          const uint32_t b_last = (uint32_t)count * a.n_var * 4u;
-          const uint32_t b_fixed = (uint32_t)count * a.n_fixed * 4u;
+          const uint32_t b_last = (uint32_t)count * a.dm.n_var * 4u;
+          const uint32_t b_fixed = (uint32_t)count * a.dm.n_fixed * 4u;
           mbar_arrive_expect_tx(&full[stage], b_in + b_last + b_fixed);
           bulk_g2s(s_in, gi, b_in, &full[stage]);
           bulk_g2s(s_last, gl, b_last, &full[stage]);
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
         }
       } else {
         for (int i = lane; i < count * a.in_row; i += 32) s_in[i] = gi[i];
-        for (int i = lane; i < count * a.n_var; i += 32) s_last[i] = gl[i];
-        for (int i = lane; i < count * a.n_fixed; i += 32) s_fixed[i] = gf[i];
+        for (int i = lane; i < count * a.dm.n_var; i += 32) s_last[i] = gl[i];
+        for (int i = lane; i < count * a.dm.n_fixed; i += 32) s_fixed[i] = gf[i];
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
       }
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
   constexpr int GPW = 32 / G;
   const int gid = warp * GPW + (lane / G);
   Solver<G> sv;
-  sv.init(a.table, st, scratch_base + (size_t)gid * Scratch<G>::kFloats, a.prm, lane);
+  sv.init(a.table, st, a.dm, scratch_base + (size_t)gid * Scratch<G>::kFloats, a.prm, lane);
 
   int it = 0;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
@@ -138,13 +138,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
       FrameInputs in;
       in.kp = by_kp ? s_in + ci * a.in_row : nullptr;
       in.ref = by_kp ? nullptr : s_in + ci * a.in_row;
-      in.last = s_last + ci * a.n_var;
-      in.fixed = s_fixed + ci * a.n_fixed;
-      in.projected = a.io.projected ? a.io.projected + f * a.len_proj : nullptr;
+      in.last = s_last + ci * a.dm.n_var;
+      in.fixed = s_fixed + ci * a.dm.n_fixed;
+      in.projected = a.io.projected ? a.io.projected + f * a.dm.len_proj : nullptr;
       const int status = sv.solve(in, active);
       if (active) {
-        if (sv.var >= 0) a.io.qpos_out[f * a.n_var + sv.var] = sv.x;
-        if (a.io.robot_qpos_out && sv.l < a.dof) a.io.robot_qpos_out[f * a.dof + sv.l] = sv.q;
+        if (sv.var >= 0) a.io.qpos_out[f * a.dm.n_var + sv.var] = sv.x;
+        if (a.io.robot_qpos_out && sv.l < a.dm.dof) a.io.robot_qpos_out[f * a.dm.dof + sv.l] = sv.q;
         if (sv.l == 0) {
           if (a.io.status_out) a.io.status_out[f] = status;
           if (a.io.cost_out) a.io.cost_out[f] = sv.F;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   float* scratch = scratch_base + (size_t)gid * (Scratch<G>::kFloats + 64);
   float* kpbuf = scratch + Scratch<G>::kFloats;  // 63 floats, this group's current keypoints
   Solver<G> sv;
-  sv.init(a.table, st, scratch, a.prm, lane);
+  sv.init(a.table, st, a.dm, scratch, a.prm, lane);
   const int l = sv.l;
   const bool use_filter = a.prm.lp_alpha >= 0.f && a.prm.lp_alpha <= 1.f;
 
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
     const long long sc = active ? s : a.S - 1;
     float last = 0.f, fy = 0.f;
     int finit = 0;
-    if (active && sv.var >= 0) last = a.io.last_qpos[sc * a.n_var + sv.var];
-    if (active && use_filter && l < a.dof) fy = a.io.filter_state[sc * a.dof + l];
+    if (active && sv.var >= 0) last = a.io.last_qpos[sc * a.dm.n_var + sv.var];
+    if (active && use_filter && l < a.dm.dof) fy = a.io.filter_state[sc * a.dm.dof + l];
     if (active && use_filter) finit = a.io.filter_init[sc];
     const float* kp_stream = a.io.keypoints + sc * a.steps * (3 * DEXR_NUM_KEYPOINTS);
     float pre[KPL];
@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
       FrameInputs in;
       in.kp = kpbuf;
       in.ref = nullptr;
-      in.fixed = a.n_fixed > 0 ? a.io.fixed_qpos + (sc * a.steps + t) * a.n_fixed : nullptr;
+      in.fixed = a.dm.n_fixed > 0 ? a.io.fixed_qpos + (sc * a.steps + t) * a.dm.n_fixed : nullptr;
       in.last = nullptr;  // warm start comes from the register `x` (previous solution)
-      in.projected = a.io.projected ? a.io.projected + sc * a.len_proj : nullptr;
+      in.projected = a.io.projected ? a.io.projected + sc * a.dm.len_proj : nullptr;
       sv.x = last;
       const int status = sv.solve(in, active);
       last = sv.x;  // unfiltered solution is the next warm start (seq_retarget.py:124)
@@ -229,14 +229,14 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
         out = fy;
       }
       if (active) {
-        if (l < a.dof) a.io.robot_qpos_out[(sc * a.steps + t) * a.dof + l] = out;
+        if (l < a.dm.dof) a.io.robot_qpos_out[(sc * a.steps + t) * a.dm.dof + l] = out;
         if (l == 0 && a.io.status_out) a.io.status_out[sc * a.steps + t] = status;
       }
       __syncwarp();
     }
     if (active) {
-      if (sv.var >= 0) a.io.last_qpos[sc * a.n_var + sv.var] = last;
-      if (use_filter && l < a.dof) a.io.filter_state[sc * a.dof + l] = fy;
+      if (sv.var >= 0) a.io.last_qpos[sc * a.dm.n_var + sv.var] = last;
+      if (use_filter && l < a.dm.dof) a.io.filter_state[sc * a.dm.dof + l] = fy;
       if (use_filter && l == 0) a.io.filter_init[sc] = (uint8_t)finit;
     }
   }
@@ -397,6 +397,14 @@ static int check_params(const dexr_params_t* p) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+static Dims make_dims(const dexr_table_t& t) {
+  Dims d;
+  d.dof = t.dof; d.n_var = t.n_var; d.n_fixed = t.n_fixed; d.n_links = t.n_links; d.n_res = t.n_res; d.loss = t.loss;
+  d.n_rounds = t.n_rounds; d.has_mimic = t.has_mimic; d.num_fingers = t.num_fingers; d.len_proj = t.len_proj;
+  d.len_s1 = t.len_s1;
+  return d;
+}
+
 template <int G>
 static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
   const dexr_table_t& t = r->host;
@@ -405,7 +413,7 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   a.prm = *prm;
   a.io = *io;
   a.B = B;
-  a.n_var = t.n_var; a.n_fixed = t.n_fixed; a.dof = t.dof; a.len_proj = t.len_proj;
+  a.dm = make_dims(t);
   a.in_row = io->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
   const int slots = r->num_sms;  // one CTA per SM
   long long per = (B + slots - 1) / slots;
@@ -463,7 +471,7 @@ static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_
   a.io = *io;
   a.S = S;
   a.steps = steps;
-  a.n_var = t.n_var; a.n_fixed = t.n_fixed; a.dof = t.dof; a.len_proj = t.len_proj;
+  a.dm = make_dims(t);
   a.scratch_off = round_up((int)sizeof(SharedTable), 16);
   constexpr int GPW = 32 / G;
   const int groups = kSeqNW * GPW;

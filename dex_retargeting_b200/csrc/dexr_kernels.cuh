@@ -113,6 +113,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Problem dimensions: passed as kernel arguments (constant bank) so that every loop bound and branch that
+// depends on them is provably warp-uniform for the compiler (no divergence scaffolding around shuffles).
+struct Dims {
+  int dof, n_var, n_fixed, n_links, n_res, loss, n_rounds, has_mimic, num_fingers, len_proj, len_s1;
+};
+
 // ------------------------------------------------------------------------------------------------
 // uniform (per CTA) slice of the robot table kept in shared memory
 // ------------------------------------------------------------------------------------------------
@@ -124,7 +130,6 @@ struct SharedTable {
   int group_count[DEXR_MAX_LANES];
   int group_lane[DEXR_MAX_LANES][DEXR_MAX_GROUP];
   float group_mult[DEXR_MAX_LANES][DEXR_MAX_GROUP];
-  int dof, n_var, n_fixed, n_links, n_res, loss, n_rounds, has_mimic, num_fingers, len_proj, len_s1;
 };
 
 __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __restrict__ tb) {
@@ -147,11 +152,6 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
       st.group_lane[i][f] = tb->group_lane[i][f];
       st.group_mult[i][f] = tb->group_mult[i][f];
     }
-  }
-  if (threadIdx.x == 0) {
-    st.dof = tb->dof; st.n_var = tb->n_var; st.n_fixed = tb->n_fixed; st.n_links = tb->n_links;
-    st.n_res = tb->n_res; st.loss = tb->loss; st.n_rounds = tb->n_rounds; st.has_mimic = tb->has_mimic;
-    st.num_fingers = tb->num_fingers; st.len_proj = tb->len_proj; st.len_s1 = tb->len_s1;
   }
 }
 
@@ -196,6 +196,7 @@ struct Solver {
   int l;     // lane within group
   int lane;  // lane within warp
   const SharedTable* st;
+  Dims dm;
   float* sc;  // group scratch
   dexr_params_t prm;
   float inv_beta;
@@ -206,9 +207,9 @@ struct Solver {
   float F;                    // objective at x
   int cur;                    // which link-position buffer holds the accepted positions
 
-  __device__ void init(const dexr_table_t* __restrict__ tb, const SharedTable* st_, float* scratch,
+  __device__ void init(const dexr_table_t* __restrict__ tb, const SharedTable* st_, const Dims& dm_, float* scratch,
                        const dexr_params_t& prm_, int lane_) {
-    st = st_; sc = scratch; prm = prm_; lane = lane_; l = lane_ & (G - 1);
+    st = st_; dm = dm_; sc = scratch; prm = prm_; lane = lane_; l = lane_ & (G - 1);
     inv_beta = 1.0f / prm.huber_delta;
     const int c = l < DEXR_MAX_LANES ? l : 0;
 #pragma unroll
@@ -255,7 +256,7 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < 3; ++i) po[i] = fmaf(qv, d0[i], p0[i]);
     }
-    const int rounds = st->n_rounds;
+    const int rounds = dm.n_rounds;
     for (int r = 0; r < rounds; ++r) {
       const int src = (jump >> (6 * r)) & 63;
       const bool has = src != 63;
@@ -285,7 +286,7 @@ struct Solver {
   // Link origins (robot_wrapper.py:85-87 [updateFramePlacement]) -> shared buffer b.
   __device__ __forceinline__ void write_links(const float* Rw, const float* pw, int b) const {
     float4* out = lp(b);
-    const int L = st->n_links;
+    const int L = dm.n_links;
     for (int k = 0; k < L; ++k) {
       const float4 o = st->link_off[k];
       const int par = __float_as_int(o.w);
@@ -303,7 +304,7 @@ struct Solver {
   // 263-274, 524-541, with the regulariser the reference only puts into the gradient).
   __device__ __forceinline__ float cost(int b, float xv) const {
     float v = 0.f;
-    const int m = st->n_res;
+    const int m = dm.n_res;
     if (l < m) {
       const float4 T = fr()[l];
       const int ti = st->res_task[l], oi = st->res_origin[l];
@@ -314,7 +315,7 @@ struct Solver {
         rx -= po.x; ry -= po.y; rz -= po.z;
       }
       const float beta = prm.huber_delta;
-      if (st->loss == DEXR_LOSS_POSITION) {
+      if (dm.loss == DEXR_LOSS_POSITION) {
         v = T.w * (huber_val(fabsf(rx), beta, inv_beta) + huber_val(fabsf(ry), beta, inv_beta) +
                    huber_val(fabsf(rz), beta, inv_beta));
       } else {
@@ -331,8 +332,8 @@ struct Solver {
   // Per-frame targets and weights -> fr[k]; DexPilot flag update (optimizer.py:460-508).
   // Returns false if an input is non finite.
   __device__ __forceinline__ bool prepare_targets(const FrameInputs& in, bool active) {
-    const int m = st->n_res;
-    const int loss = st->loss;
+    const int m = dm.n_res;
+    const int loss = dm.loss;
     float tx = 0.f, ty = 0.f, tz = 0.f, w = 0.f;
     if (active && l < m) {
       if (in.kp != nullptr) {
@@ -350,7 +351,7 @@ struct Solver {
       tx *= prm.scaling; ty *= prm.scaling; tz *= prm.scaling;
       w = 1.0f / m;
     } else {
-      const int len_proj = st->len_proj, len_s1 = st->len_s1;
+      const int len_proj = dm.len_proj, len_s1 = dm.len_s1;
       const float dist = sqrtf(fmaf(tx, tx, fmaf(ty, ty, tz * tz)));
       int flag = 0;
       if (l < len_s1) {
@@ -374,7 +375,7 @@ struct Solver {
         }
         if (active && in.projected != nullptr) in.projected[l] = (uint8_t)flag;
       } else {
-        weight = (float)(len_proj + st->num_fingers);
+        weight = (float)(len_proj + dm.num_fingers);
         tx *= prm.scaling; ty *= prm.scaling; tz *= prm.scaling;
       }
       w = weight / m;
@@ -387,7 +388,7 @@ struct Solver {
   // One frame.  Returns status word.  On exit x (var lanes) and q (all lanes) hold the solution.
   // ---------------------------------------------------------------------------------------------
   __device__ __forceinline__ int solve(const FrameInputs& in, bool active) {
-    const int dof = st->dof;
+    const int dof = dm.dof;
     const float nd = prm.norm_delta;
     const float beta = prm.huber_delta;
     int status = 0;
@@ -441,8 +442,8 @@ struct Solver {
       a[1] = fmaf(R[3], ax[0], fmaf(R[4], ax[1], R[5] * ax[2]));
       a[2] = fmaf(R[6], ax[0], fmaf(R[7], ax[1], R[8] * ax[2]));
       const bool rev = jtype == 0;
-      const int m = st->n_res;
-      const int loss = st->loss;
+      const int m = dm.n_res;
+      const int loss = dm.loss;
       const float4* lpc = lp(cur);
       float rmax = 0.f;
       for (int k = 0; k < m; ++k) {
@@ -533,7 +534,7 @@ struct Solver {
         }
       }
       // ---- mimic fold: H_x = M^T H_q M, g_x = M^T g_q (kinematics_adaptor.py:107-113) ----
-      if (st->has_mimic) {
+      if (dm.has_mimic) {
         const float ml = var >= 0 ? 1.0f : (msrc >= 0 ? mmult : 0.f);
         float* hbuf = hb();
         __syncwarp();
@@ -553,15 +554,16 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
         __syncwarp();
-#pragma unroll
-        for (int s = 0; s < NP; ++s) {
+        // row fold through shared memory (runtime loop: keeps the code small; only mimic robots get here)
+        float* hrow = lrow();  // free at this point: jbuf / at are no longer read
+        for (int s = 0; s < dof; ++s) {
           float acc = 0.f;
-          if (s < dof) {
-            const int cnt = st->group_count[s];
-            for (int f = 0; f < cnt; ++f) acc = fmaf(st->group_mult[s][f], hbuf[st->group_lane[s][f] * NP + l], acc);
-          }
-          H[s] = acc;
+          const int cnt = st->group_count[s];
+          for (int f = 0; f < cnt; ++f) acc = fmaf(st->group_mult[s][f], hbuf[st->group_lane[s][f] * NP + l], acc);
+          hrow[s * NP + l] = acc;
         }
+#pragma unroll
+        for (int s = 0; s < NP; ++s) H[s] = (s < dof) ? hrow[s * NP + l] : 0.f;
         float gx_ = 0.f;
 #pragma unroll
         for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
