@@ -47,13 +47,12 @@ struct SeqArgs {
 // ------------------------------------------------------------------------------------------------
 template <int G, int NCW>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const FrameArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = dsmem;
   SharedTable* st = reinterpret_cast<SharedTable*>(smem);
   unsigned char* ring = smem + a.ring_off;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* empty = full + 2;
   int* next = reinterpret_cast<int*>(empty + 2);
-  float* scratch_base = reinterpret_cast<float*>(smem + a.scratch_off);
 
   load_shared_table(*st, a.table);
   if (threadIdx.x == 0) {
@@ -114,7 +113,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
   constexpr int GPW = 32 / G;
   const int gid = warp * GPW + (lane / G);
   Solver<G> sv;
-  sv.init(a.table, st, a.dm, scratch_base + (size_t)gid * Scratch<G>::kFloats, a.prm, lane);
+  sv.init(a.table, a.dm, (uint32_t)(a.scratch_off + gid * Scratch<G>::kFloats * 4), a.prm, lane);
 
   int it = 0;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
@@ -161,9 +160,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
 // ------------------------------------------------------------------------------------------------
 template <int G, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* const smem = dsmem;
   SharedTable* st = reinterpret_cast<SharedTable*>(smem);
-  float* scratch_base = reinterpret_cast<float*>(smem + a.scratch_off);
   load_shared_table(*st, a.table);
   __syncthreads();
 
@@ -173,10 +171,10 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   const int lane = threadIdx.x & 31;
   const int gid = warp * GPW + (lane / G);
   const int groups_per_cta = NW * GPW;
-  float* scratch = scratch_base + (size_t)gid * (Scratch<G>::kFloats + 64);
-  float* kpbuf = scratch + Scratch<G>::kFloats;  // 63 floats, this group's current keypoints
+  const uint32_t scratch_off = (uint32_t)(a.scratch_off + gid * (Scratch<G>::kFloats + 64) * 4);
+  float* kpbuf = reinterpret_cast<float*>(smem + scratch_off) + Scratch<G>::kFloats;  // 63 floats: current keypoints
   Solver<G> sv;
-  sv.init(a.table, st, a.dm, scratch, a.prm, lane);
+  sv.init(a.table, a.dm, scratch_off, a.prm, lane);
   const int l = sv.l;
   const bool use_filter = a.prm.lp_alpha >= 0.f && a.prm.lp_alpha <= 1.f;
 
@@ -278,7 +276,7 @@ struct dexr_robot {
   size_t stage_bytes = 0;
 };
 
-constexpr int kFramesNCW = 11;  // consumer warps per CTA (frames kernel)
+template <int G> struct FramesCfg { static constexpr int NCW = (G == 16) ? 15 : 11; };  // consumer warps per CTA
 constexpr int kSeqNW = 8;       // warps per CTA (sequences kernel)
 constexpr int kMaxTile = 64;
 
@@ -432,13 +430,14 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   a.bar_off = a.ring_off + 2 * a.stage_bytes;
   a.scratch_off = round_up(a.bar_off + 4 * 8 + 2 * 4, 16);
   constexpr int GPW = 32 / G;
-  const int smem = a.scratch_off + kFramesNCW * GPW * Scratch<G>::kFloats * 4;
-  auto kern = dexr_frames_kernel<G, kFramesNCW>;
+  constexpr int NCW = FramesCfg<G>::NCW;
+  const int smem = a.scratch_off + NCW * GPW * Scratch<G>::kFloats * 4;
+  auto kern = dexr_frames_kernel<G, NCW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(a.ntiles, slots);
-  kern<<<grid, (kFramesNCW + 1) * 32, smem, stream>>>(a);
+  kern<<<grid, (NCW + 1) * 32, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
-  r->last = dexr_launch_info_t{grid, (kFramesNCW + 1) * 32, smem, T, G, kFramesNCW, r->last.kernels_launched + 1};
+  r->last = dexr_launch_info_t{grid, (NCW + 1) * 32, smem, T, G, NCW, r->last.kernels_launched + 1};
   return 0;
 }
 

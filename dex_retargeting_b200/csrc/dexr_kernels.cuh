@@ -30,6 +30,10 @@
 
 namespace dexr {
 
+// The whole dynamic shared memory of a CTA.  Declared once at namespace scope so that every access below is
+// a shared-window access with a compile-time offset (LDS/STS [reg + imm]) instead of a generic pointer.
+extern __shared__ __align__(16) unsigned char dsmem[];
+
 constexpr int kMaxTrials = 8;
 constexpr float kNoise = 2e-6f;      // relative fp32 noise floor of the objective value
 constexpr float kLamMin = 1e-7f;
@@ -123,6 +127,11 @@ struct Dims {
 // uniform (per CTA) slice of the robot table kept in shared memory
 // ------------------------------------------------------------------------------------------------
 struct SharedTable {
+  // per lane, element i of the 3x3 joint placement: (R0[i], RA[i], RB[i], w) with w = p0[i] (i<3), d0[i-3]
+  // (3<=i<6), axis[i-6] (6<=i<9); [i][lane] so that a group's LDS.128 is conflict free
+  float4 lane_c[9][DEXR_MAX_LANES];
+  float clip_lo[DEXR_MAX_LANES], clip_hi[DEXR_MAX_LANES];
+  int fixed_index[DEXR_MAX_LANES];
   float4 link_off[DEXR_MAX_LINKS];  // xyz, w = parent lane as int bits
   uint32_t link_anc[DEXR_MAX_LINKS];
   int res_task[DEXR_MAX_RES], res_origin[DEXR_MAX_RES], res_ht[DEXR_MAX_RES], res_ho[DEXR_MAX_RES];
@@ -147,6 +156,13 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
     st.s2_task[i] = tb->s2_task[i];
   }
   for (int i = threadIdx.x; i < DEXR_MAX_LANES; i += blockDim.x) {
+    for (int e = 0; e < 9; ++e) {
+      const float w = e < 3 ? tb->p0[i][e] : (e < 6 ? tb->d0[i][e - 3] : tb->axis[i][e - 6]);
+      st.lane_c[e][i] = make_float4(tb->R0[i][e], tb->RA[i][e], tb->RB[i][e], w);
+    }
+    st.clip_lo[i] = tb->clip_lo[i];
+    st.clip_hi[i] = tb->clip_hi[i];
+    st.fixed_index[i] = tb->fixed_index[i];
     st.group_count[i] = tb->group_count[i];
     for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
       st.group_lane[i][f] = tb->group_lane[i][f];
@@ -186,18 +202,14 @@ struct Solver {
   static constexpr int NP = G;
   using SC = Scratch<G>;
 
-  // ---- lane constants (whole kernel) ----
-  float R0[9], RA[9], RB[9], p0[3], d0[3], ax[3];
-  float lo, hi, clo, chi, mmult, moff;
-  int jtype, var, fixedi, msrc;
+  // ---- lane constants kept in registers (the 3x4 joint placement lives in shared memory) ----
+  float lo, hi, mmult, moff;
+  int jtype, var, msrc;
   uint32_t jump, anc, desc;
-  int gcount, glane[DEXR_MAX_GROUP];
-  float gmult[DEXR_MAX_GROUP];
   int l;     // lane within group
   int lane;  // lane within warp
-  const SharedTable* st;
+  uint32_t sc_off;  // byte offset of this group's scratch inside dsmem
   Dims dm;
-  float* sc;  // group scratch
   dexr_params_t prm;
   float inv_beta;
 
@@ -207,31 +219,27 @@ struct Solver {
   float F;                    // objective at x
   int cur;                    // which link-position buffer holds the accepted positions
 
-  __device__ void init(const dexr_table_t* __restrict__ tb, const SharedTable* st_, const Dims& dm_, float* scratch,
+  __device__ __forceinline__ static const SharedTable& ST() { return *reinterpret_cast<const SharedTable*>(dsmem); }
+
+  __device__ void init(const dexr_table_t* __restrict__ tb, const Dims& dm_, uint32_t scratch_byte_off,
                        const dexr_params_t& prm_, int lane_) {
-    st = st_; dm = dm_; sc = scratch; prm = prm_; lane = lane_; l = lane_ & (G - 1);
+    dm = dm_; sc_off = scratch_byte_off; prm = prm_; lane = lane_; l = lane_ & (G - 1);
     inv_beta = 1.0f / prm.huber_delta;
-    const int c = l < DEXR_MAX_LANES ? l : 0;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { R0[i] = tb->R0[c][i]; RA[i] = tb->RA[c][i]; RB[i] = tb->RB[c][i]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { p0[i] = tb->p0[c][i]; d0[i] = tb->d0[c][i]; ax[i] = tb->axis[c][i]; }
-    lo = tb->lower[c]; hi = tb->upper[c]; clo = tb->clip_lo[c]; chi = tb->clip_hi[c];
+    const int c = l;
+    lo = tb->lower[c]; hi = tb->upper[c];
     mmult = tb->mimic_mult[c]; moff = tb->mimic_off[c];
-    jtype = tb->jtype[c]; var = tb->var_index[c]; fixedi = tb->fixed_index[c]; msrc = tb->mimic_src[c];
+    jtype = tb->jtype[c]; var = tb->var_index[c]; msrc = tb->mimic_src[c];
     jump = tb->jump[c]; anc = tb->anc_mask[c]; desc = tb->desc_mask[c];
-    gcount = tb->group_count[c];
-#pragma unroll
-    for (int f = 0; f < DEXR_MAX_GROUP; ++f) { glane[f] = tb->group_lane[c][f]; gmult[f] = tb->group_mult[c][f]; }
   }
 
-  __device__ __forceinline__ float4* fr() const { return reinterpret_cast<float4*>(sc + SC::kFr); }
-  __device__ __forceinline__ float4* lp(int b) const { return reinterpret_cast<float4*>(sc + SC::kLp) + b * DEXR_MAX_LINKS; }
-  __device__ __forceinline__ float* jbuf(int b, int comp) const { return sc + SC::kU + (b * 3 + comp) * NP; }
-  __device__ __forceinline__ float4* at() const { return reinterpret_cast<float4*>(sc + SC::kU + 6 * NP); }
-  __device__ __forceinline__ float* lrow() const { return sc + SC::kU; }
-  __device__ __forceinline__ float* hb() const { return sc + SC::kHb; }
-  __device__ __forceinline__ float* lcol() const { return sc + SC::kLcol; }
+  __device__ __forceinline__ float* scf() const { return reinterpret_cast<float*>(dsmem + sc_off); }
+  __device__ __forceinline__ float4* fr() const { return reinterpret_cast<float4*>(scf() + SC::kFr); }
+  __device__ __forceinline__ float4* lp(int b) const { return reinterpret_cast<float4*>(scf() + SC::kLp) + b * DEXR_MAX_LINKS; }
+  __device__ __forceinline__ float* jbuf(int b, int comp) const { return scf() + SC::kU + (b * 3 + comp) * NP; }
+  __device__ __forceinline__ float4* at() const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP); }
+  __device__ __forceinline__ float* lrow() const { return scf() + SC::kU; }
+  __device__ __forceinline__ float* hb() const { return scf() + SC::kHb; }
+  __device__ __forceinline__ float* lcol() const { return scf() + SC::kLcol; }
 
   // q of every joint from the variables: target joints copy, fixed joints constant, mimic affine.
   // (optimizer.py:147-151 + kinematics_adaptor.py:102-105)
@@ -245,17 +253,16 @@ struct Solver {
     float s, c;
     sincosf(qv, &s, &c);
     const float omc = 1.0f - c;
-    if (jtype == 0) {
+    const bool rev = jtype == 0;
+    float w[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) Ro[i] = fmaf(s, RA[i], fmaf(omc, RB[i], R0[i]));
-#pragma unroll
-      for (int i = 0; i < 3; ++i) po[i] = p0[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Ro[i] = R0[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) po[i] = fmaf(qv, d0[i], p0[i]);
+    for (int i = 0; i < 9; ++i) {
+      const float4 k = ST().lane_c[i][l];
+      Ro[i] = rev ? fmaf(s, k.y, fmaf(omc, k.z, k.x)) : k.x;
+      w[i] = k.w;
     }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) po[i] = rev ? w[i] : fmaf(qv, w[3 + i], w[i]);
     const int rounds = dm.n_rounds;
     for (int r = 0; r < rounds; ++r) {
       const int src = (jump >> (6 * r)) & 63;
@@ -288,7 +295,7 @@ struct Solver {
     float4* out = lp(b);
     const int L = dm.n_links;
     for (int k = 0; k < L; ++k) {
-      const float4 o = st->link_off[k];
+      const float4 o = ST().link_off[k];
       const int par = __float_as_int(o.w);
       if (par == l) {
         out[k] = make_float4(fmaf(Rw[0], o.x, fmaf(Rw[1], o.y, fmaf(Rw[2], o.z, pw[0]))),
@@ -307,7 +314,7 @@ struct Solver {
     const int m = dm.n_res;
     if (l < m) {
       const float4 T = fr()[l];
-      const int ti = st->res_task[l], oi = st->res_origin[l];
+      const int ti = ST().res_task[l], oi = ST().res_origin[l];
       const float4 pt = lp(b)[ti];
       float rx = pt.x - T.x, ry = pt.y - T.y, rz = pt.z - T.z;
       if (oi >= 0) {
@@ -337,7 +344,7 @@ struct Solver {
     float tx = 0.f, ty = 0.f, tz = 0.f, w = 0.f;
     if (active && l < m) {
       if (in.kp != nullptr) {
-        const int ht = st->res_ht[l], ho = st->res_ho[l];
+        const int ht = ST().res_ht[l], ho = ST().res_ho[l];
         tx = in.kp[3 * ht]; ty = in.kp[3 * ht + 1]; tz = in.kp[3 * ht + 2];
         if (ho >= 0) { tx -= in.kp[3 * ho]; ty -= in.kp[3 * ho + 1]; tz -= in.kp[3 * ho + 2]; }
       } else {
@@ -361,7 +368,7 @@ struct Solver {
       }
       const int k2 = l - len_s1;
       const bool is_s2 = (l >= len_s1) && (l < len_proj);
-      const int so = is_s2 ? st->s2_origin[k2] : 0, sk = is_s2 ? st->s2_task[k2] : 0;
+      const int so = is_s2 ? ST().s2_origin[k2] : 0, sk = is_s2 ? ST().s2_task[k2] : 0;
       const int fo = gshfl_i<G>(flag, so), fk_ = gshfl_i<G>(flag, sk);
       if (is_s2) flag = (fo && fk_ && dist <= 0.03f) ? 1 : 0;
       float weight;
@@ -397,9 +404,10 @@ struct Solver {
     float xin = 0.f;
     if (in.last == nullptr) xin = var >= 0 ? x : 0.f;  // sequences: previous solution kept in registers
     else if (active && var >= 0) xin = in.last[var];
-    if (prm.clip_init && var >= 0) xin = fminf(fmaxf(xin, clo), chi);
+    if (prm.clip_init && var >= 0) xin = fminf(fmaxf(xin, ST().clip_lo[l]), ST().clip_hi[l]);
     x0 = xin;
     x = fminf(fmaxf(xin, lo), hi);
+    const int fixedi = ST().fixed_index[l];
     qfix = (active && fixedi >= 0) ? in.fixed[fixedi] : 0.f;
     bool finite = isfinite(xin) && isfinite(qfix);
     const bool ok_in = prepare_targets(in, active);
@@ -438,19 +446,22 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < NP; ++i) H[i] = 0.f;
       float g = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
-      a[0] = fmaf(R[0], ax[0], fmaf(R[1], ax[1], R[2] * ax[2]));
-      a[1] = fmaf(R[3], ax[0], fmaf(R[4], ax[1], R[5] * ax[2]));
-      a[2] = fmaf(R[6], ax[0], fmaf(R[7], ax[1], R[8] * ax[2]));
+      {
+        const float ax0 = ST().lane_c[6][l].w, ax1 = ST().lane_c[7][l].w, ax2 = ST().lane_c[8][l].w;
+        a[0] = fmaf(R[0], ax0, fmaf(R[1], ax1, R[2] * ax2));
+        a[1] = fmaf(R[3], ax0, fmaf(R[4], ax1, R[5] * ax2));
+        a[2] = fmaf(R[6], ax0, fmaf(R[7], ax1, R[8] * ax2));
+      }
       const bool rev = jtype == 0;
       const int m = dm.n_res;
       const int loss = dm.loss;
       const float4* lpc = lp(cur);
       float rmax = 0.f;
       for (int k = 0; k < m; ++k) {
-        const int ti = st->res_task[k], oi = st->res_origin[k];
+        const int ti = ST().res_task[k], oi = ST().res_origin[k];
         const float4 T = fr()[k];
         const float4 pt = lpc[ti];
-        const uint32_t mt = st->link_anc[ti];
+        const uint32_t mt = ST().link_anc[ti];
         float rx = pt.x - T.x, ry = pt.y - T.y, rz = pt.z - T.z;
         float j0 = 0.f, j1 = 0.f, j2 = 0.f;
         if ((mt >> l) & 1u) {
@@ -462,7 +473,7 @@ struct Solver {
         uint32_t mo = 0u;
         if (oi >= 0) {
           const float4 po = lpc[oi];
-          mo = st->link_anc[oi];
+          mo = ST().link_anc[oi];
           rx -= po.x; ry -= po.y; rz -= po.z;
           if ((mo >> l) & 1u) {
             if (rev) {
@@ -543,9 +554,10 @@ struct Solver {
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < NP; ++i) H[i] = 0.f;
+        const int gcount = ST().group_count[l];
         for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
           if (var >= 0 && f < gcount) {
-            const int cl = glane[f];
+            const int cl = ST().group_lane[l][f];
 #pragma unroll
             for (int i = 0; i < NP; ++i) H[i] += hbuf[i * NP + cl];
           }
@@ -558,8 +570,8 @@ struct Solver {
         float* hrow = lrow();  // free at this point: jbuf / at are no longer read
         for (int s = 0; s < dof; ++s) {
           float acc = 0.f;
-          const int cnt = st->group_count[s];
-          for (int f = 0; f < cnt; ++f) acc = fmaf(st->group_mult[s][f], hbuf[st->group_lane[s][f] * NP + l], acc);
+          const int cnt = ST().group_count[s];
+          for (int f = 0; f < cnt; ++f) acc = fmaf(ST().group_mult[s][f], hbuf[ST().group_lane[s][f] * NP + l], acc);
           hrow[s * NP + l] = acc;
         }
 #pragma unroll
@@ -568,8 +580,8 @@ struct Solver {
 #pragma unroll
         for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
           const bool v = var >= 0 && f < gcount;
-          const float gv = gshfl<G>(g, v ? glane[f] : l);
-          if (v) gx_ = fmaf(gmult[f], gv, gx_);
+          const float gv = gshfl<G>(g, v ? ST().group_lane[l][f] : l);
+          if (v) gx_ = fmaf(ST().group_mult[l][f], gv, gx_);
         }
         g = gx_;
         __syncwarp();
