@@ -41,7 +41,7 @@ BYTES_PER_FRAME = 21 * 3 * 4 + 16 * 4 + 16 * 4  # keypoints in + warm start in +
 
 
 # --------------------------------------------------------------------------------------- data
-def make_batch(kin, opt_cfg, n, seed):
+def make_batch(kin, opt_cfg, n, seed, centre=True):
     """Synthetic keypoint frames + warm starts (numpy, host)."""
     rng = np.random.RandomState(seed)
     lim = kin.joint_limits
@@ -62,8 +62,12 @@ def make_batch(kin, opt_cfg, n, seed):
         else:
             Rb = np.broadcast_to(kin.joint_R[i], (n, 3, 3))
             pb = np.broadcast_to(kin.joint_p[i], (n, 3))
-        Rw[:, i] = Rb @ Rq
-        pw[:, i] = pb
+        if kin.joint_type[i] == 0:
+            Rw[:, i] = Rb @ Rq
+            pw[:, i] = pb
+        else:  # prismatic
+            Rw[:, i] = Rb
+            pw[:, i] = pb + np.einsum("bij,j->bi", Rb, a) * q[:, i:i + 1]
     kp = np.zeros((n, 21, 3), dtype=np.float32)
     names, human, scale = opt_cfg
     for name, h in zip(names, human):
@@ -74,8 +78,8 @@ def make_batch(kin, opt_cfg, n, seed):
         else:
             pos = np.broadcast_to(kin.link_p[li], (n, 3))
         kp[:, h] = (pos / scale).astype(np.float32)
-    # make the origin (wrist) the zero of the keypoint frame, like a wrist-centred detector output
-    kp -= kp[:, 0:1].copy()
+    if centre:  # make the origin (wrist) the zero of the keypoint frame, like a wrist-centred detector output
+        kp -= kp[:, 0:1].copy()
     return kp, init
 
 

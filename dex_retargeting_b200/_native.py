@@ -73,6 +73,7 @@ EXPORTS = [
     "dexr_version", "dexr_last_error", "dexr_table_sizeof", "dexr_params_sizeof", "dexr_default_params",
     "dexr_robot_create", "dexr_robot_create_from_device", "dexr_robot_device_table", "dexr_robot_destroy",
     "dexr_solve_frames", "dexr_solve_sequences", "dexr_solve_frames_host", "dexr_get_launch_info",
+    "dexr_preprocess_keypoints",
 ]
 
 _LIB = None
@@ -116,6 +117,7 @@ def load():
                                          C.c_int64, C.c_void_p]
     lib.dexr_solve_frames_host.argtypes = [C.c_void_p, C.POINTER(DexrParams), C.POINTER(DexrFrames), C.c_int64]
     lib.dexr_get_launch_info.argtypes = [C.c_void_p, C.POINTER(DexrLaunchInfo)]
+    lib.dexr_preprocess_keypoints.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]
     if lib.dexr_table_sizeof() != C.sizeof(DexrTable):
         raise DexrError(f"dexr_table_t layout mismatch: library {lib.dexr_table_sizeof()} vs binding {C.sizeof(DexrTable)}")
     if lib.dexr_params_sizeof() != C.sizeof(DexrParams):

@@ -240,6 +240,80 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// keypoint pre-processing (single_hand_detector.py:100-103, 130-158): one thread per frame for the 3x3 frame,
+// tile staged through shared memory so that global loads / stores are coalesced 16-byte accesses
+// ------------------------------------------------------------------------------------------------
+constexpr int kPreTile = 128;  // frames per CTA tile; 128 * 252 B = 32256 B, a multiple of 16
+
+__global__ void __launch_bounds__(kPreTile) dexr_preprocess_kernel(const float* __restrict__ raw, float* __restrict__ out,
+                                                                    float* __restrict__ rot_out, int left, long long B) {
+  __shared__ __align__(16) float tile[kPreTile * 63];
+  const int tid = threadIdx.x;
+  for (long long f0 = (long long)blockIdx.x * kPreTile; f0 < B; f0 += (long long)gridDim.x * kPreTile) {
+    const int count = (int)min((long long)kPreTile, B - f0);
+    const int nfl = count * 63;
+    const float* src = raw + f0 * 63;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      for (int i = tid; i < nfl / 4; i += kPreTile) t4[i] = s4[i];
+      for (int i = (nfl / 4) * 4 + tid; i < nfl; i += kPreTile) tile[i] = src[i];
+    } else {
+      for (int i = tid; i < nfl; i += kPreTile) tile[i] = src[i];
+    }
+    __syncthreads();
+    if (tid < count) {
+      float* k = tile + tid * 63;  // stride 63 floats: odd -> conflict-free per-thread rows
+      const float wx = k[0], wy = k[1], wz = k[2];
+      // landmarks 5 (index base) and 9 (middle base) relative to the wrist
+      const float ax = k[15] - wx, ay = k[16] - wy, az = k[17] - wz;
+      const float bx = k[27] - wx, by = k[28] - wy, bz = k[29] - wz;
+      // plane normal through {wrist, index base, middle base}; the SVD of the reference gives +-this vector
+      float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+      const float nn = rsqrtf(nx * nx + ny * ny + nz * nz);
+      nx *= nn; ny *= nn; nz *= nn;
+      // x axis: wrist - middle base, orthogonalised against the normal
+      float xx = -bx, xy = -by, xz = -bz;
+      const float dn = xx * nx + xy * ny + xz * nz;
+      xx -= dn * nx; xy -= dn * ny; xz -= dn * nz;
+      const float xn = rsqrtf(xx * xx + xy * xy + xz * xz);
+      xx *= xn; xy *= xn; xz *= xn;
+      float zx = xy * nz - xz * ny, zy = xz * nx - xx * nz, zz = xx * ny - xy * nx;
+      // z should point like (index base - middle base)
+      if (zx * (ax - bx) + zy * (ay - by) + zz * (az - bz) < 0.f) { nx = -nx; ny = -ny; nz = -nz; zx = -zx; zy = -zy; zz = -zz; }
+      // frame = [x | normal | z] (columns); joint_pos = (kp - wrist) @ frame @ operator2mano
+      // operator2mano right = [[0,0,-1],[-1,0,0],[0,1,0]], left = [[0,0,-1],[1,0,0],[0,-1,0]]
+      const float sgn = left ? -1.f : 1.f;
+#pragma unroll 3
+      for (int j = 0; j < 21; ++j) {
+        const float px = k[3 * j] - wx, py = k[3 * j + 1] - wy, pz = k[3 * j + 2] - wz;
+        const float u = px * xx + py * xy + pz * xz;  // along x
+        const float v = px * nx + py * ny + pz * nz;  // along normal
+        const float w = px * zx + py * zy + pz * zz;  // along z
+        k[3 * j] = -sgn * v;
+        k[3 * j + 1] = sgn * w;
+        k[3 * j + 2] = -u;
+      }
+      if (rot_out) {
+        float* r = rot_out + (f0 + tid) * 9;
+        r[0] = xx; r[1] = nx; r[2] = zx; r[3] = xy; r[4] = ny; r[5] = zy; r[6] = xz; r[7] = nz; r[8] = zz;
+      }
+    }
+    __syncthreads();
+    float* dst = out + f0 * 63;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      const float4* t4 = reinterpret_cast<const float4*>(tile);
+      for (int i = tid; i < nfl / 4; i += kPreTile) d4[i] = t4[i];
+      for (int i = (nfl / 4) * 4 + tid; i < nfl; i += kPreTile) dst[i] = tile[i];
+    } else {
+      for (int i = tid; i < nfl; i += kPreTile) dst[i] = tile[i];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace dexr
 
 // ================================================================================================
@@ -506,6 +580,22 @@ extern "C" int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params
 }
 
 extern "C" {
+
+int dexr_preprocess_keypoints(const float* raw, float* out, float* wrist_rot_out, int hand_type, int64_t num_frames,
+                              int device, void* cuda_stream) {
+  if (!raw || !out) return fail(DEXR_E_INVALID, "dexr_preprocess_keypoints: null argument");
+  if (num_frames < 0 || (hand_type != 0 && hand_type != 1)) return fail(DEXR_E_INVALID, "bad num_frames / hand_type");
+  if (num_frames == 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const long long tiles = (num_frames + kPreTile - 1) / kPreTile;
+  const int grid = (int)std::min<long long>(tiles, (long long)sms * 8);
+  dexr_preprocess_kernel<<<grid, kPreTile, 0, static_cast<cudaStream_t>(cuda_stream)>>>(raw, out, wrist_rot_out, hand_type,
+                                                                                          (long long)num_frames);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 
 int dexr_get_launch_info(const dexr_robot_t* robot, dexr_launch_info_t* out) {
   if (!robot || !out) return fail(DEXR_E_INVALID, "null argument");

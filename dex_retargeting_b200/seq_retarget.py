@@ -108,6 +108,49 @@ class SeqRetargeting:
                 self.last_qpos[num] = pose_vec[DUMMY_JOINT_NAMES.index(name)]
         self.is_warm_started = True
 
+    def warm_start_batch(self, last_qpos, wrist_pos, wrist_quat, hand_type: HandType = HandType.right,
+                         is_mano_convention: bool = False):
+        """Batched `warm_start` (seq_retarget.py:45-110) for S streams: writes the analytic 6-D dummy-joint
+        pose into `last_qpos` [S, opt_dof] (a torch tensor on any device, e.g. `StreamState.last_qpos`) from
+        wrist positions [S,3] and quaternions [S,4] (w, x, y, z).  Pure tensor algebra, no host round trip."""
+        import torch
+
+        if wrist_pos.shape[-1] != 3 or wrist_quat.shape[-1] != 4:
+            raise ValueError("wrist_pos must be [S,3] and wrist_quat [S,4]")
+        robot = self.optimizer.robot
+        names = self.optimizer.target_joint_names
+        cols = [names.index(n) if n in names else -1 for n in DUMMY_JOINT_NAMES]
+        if min(cols) < 0:
+            raise ValueError("warm_start needs the 6 dummy free joints among the optimised joints")
+        dt, dev = last_qpos.dtype, last_qpos.device
+        # constant of the robot: root -> wrist transform with the dummy joints at zero
+        qpos = robot.q0.copy()
+        for num, name in enumerate(names):
+            if name in DUMMY_JOINT_NAMES:
+                qpos[num] = 0
+        robot.compute_forward_kinematics(qpos)
+        wrist_link_id = robot.get_joint_parent_child_frames(DUMMY_JOINT_NAMES[5])[1]
+        root2wrist = torch.as_tensor(robot.get_link_pose_inv(wrist_link_id), dtype=torch.float64, device=dev)
+        o2m = torch.as_tensor(OPERATOR2MANO[hand_type] if is_mano_convention else np.eye(3), dtype=torch.float64, device=dev)
+        q = wrist_quat.to(torch.float64)
+        q = q / q.norm(dim=-1, keepdim=True)
+        w, x, y, z = q.unbind(-1)
+        Rw = torch.stack([
+            torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+            torch.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+            torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2) @ o2m.T
+        R = Rw @ root2wrist[:3, :3]
+        t = (Rw @ root2wrist[:3, 3]) + wrist_pos.to(torch.float64)
+        sb = R[..., 0, 2].clamp(-1.0, 1.0)
+        b = torch.asin(sb)
+        regular = sb.abs() < 1 - 1e-10
+        a = torch.where(regular, torch.atan2(-R[..., 1, 2], R[..., 2, 2]), torch.atan2(R[..., 2, 1], R[..., 1, 1]))
+        c = torch.where(regular, torch.atan2(-R[..., 0, 1], R[..., 0, 0]), torch.zeros_like(b))
+        pose = torch.cat([t, torch.stack([a, b, c], -1)], dim=-1).to(dt)
+        last_qpos[:, cols] = pose
+        self.is_warm_started = True
+        return last_qpos
+
     def retarget(self, ref_value, fixed_qpos=np.array([])):
         tic = time.perf_counter()
         qpos = self.optimizer.retarget(

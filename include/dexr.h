@@ -191,6 +191,15 @@ int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params_t* params,
  * internal streams, and returns when the results are in the host buffers. */
 int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, const dexr_frames_t* io_host,
                            int64_t num_frames);
+/* Keypoint pre-processing, the step right before the hot path in the reference's teleoperation pipeline
+ * (example/vector_retargeting/single_hand_detector.py:100-103 and :130-158): centre the 21 detector landmarks at
+ * the wrist, estimate the wrist frame from landmarks {0,5,9} (plane normal + Gram-Schmidt, sign fixed by the
+ * index->middle direction), rotate into it and into the MANO convention (constants.py:7-21).
+ * raw [B,21,3] -> out [B,21,3]; wrist_rot_out [B,3,3] (the estimated frame, row-major) may be NULL.
+ * hand_type: 0 = right, 1 = left.  Degenerate (collinear) landmarks produce NaN, which the solver then flags.
+ * Independent of any robot: no handle.  HBM-bound (252 B in + 252 B out per frame). */
+int dexr_preprocess_keypoints(const float* raw, float* out, float* wrist_rot_out, int hand_type, int64_t num_frames,
+                              int device, void* cuda_stream);
 /* Launch geometry of the last call on this handle (diagnostics / bench reporting). */
 int dexr_get_launch_info(const dexr_robot_t* robot, dexr_launch_info_t* out);
 

@@ -1,0 +1,87 @@
+"""Keypoint pre-processing kernel vs the oracle restatement of the reference's detector post-processing."""
+import numpy as np
+import pytest
+
+from helpers import keypoint_trajectory
+from oracle.preprocess import preprocess
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def random_rotations(n, rng):
+    q = rng.randn(n, 4)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    return np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                     np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                     np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
+
+
+@pytest.mark.parametrize("hand", ["right", "left"])
+@pytest.mark.parametrize("B", [1, 5, 127, 128, 129, 1000])
+def test_preprocess_matches_oracle(hand, B):
+    from dex_retargeting_b200.constants import HandType
+    from dex_retargeting_b200.preprocess import preprocess_keypoints
+
+    rng = np.random.RandomState(B)
+    base = keypoint_trajectory()
+    idx = rng.randint(0, base.shape[0], size=B)
+    # undo the wrist alignment: random rigid motion of every frame, as a detector in camera coordinates would see it
+    R = random_rotations(B, rng)
+    t = rng.randn(B, 1, 3) * 0.3
+    raw = (np.einsum("bij,bkj->bki", R, base[idx].astype(np.float64)) + t).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    rot = torch.zeros((B, 3, 3), dtype=torch.float32, device=dev)
+    out = preprocess_keypoints(torch.from_numpy(raw).to(dev), HandType[hand], wrist_rot_out=rot)
+    torch.cuda.synchronize()
+    out, rot = out.cpu().numpy(), rot.cpu().numpy()
+    for b in range(B):
+        want, wrot = preprocess(raw[b], hand)
+        np.testing.assert_allclose(out[b], want, atol=2e-6)
+        np.testing.assert_allclose(rot[b], wrot, atol=2e-6)
+    # properties: wrist at the origin, rigid (pairwise distances preserved), invariant to the rigid motion applied
+    np.testing.assert_allclose(out[:, 0], 0, atol=1e-7)
+    d_in = np.linalg.norm(raw[:, 4] - raw[:, 8], axis=1)
+    d_out = np.linalg.norm(out[:, 4] - out[:, 8], axis=1)
+    np.testing.assert_allclose(d_out, d_in, atol=1e-6)
+
+
+def test_preprocess_is_invariant_to_camera_pose_and_feeds_solver():
+    """Same hand seen from two camera poses -> same processed keypoints -> same retargeting result."""
+    from helpers import build_product
+    from dex_retargeting_b200.preprocess import preprocess_keypoints
+
+    rng = np.random.RandomState(0)
+    base = keypoint_trajectory()[::7][:64].astype(np.float64)
+    dev = torch.device("cuda", 0)
+    outs = []
+    for seed in (1, 2):
+        r = np.random.RandomState(seed)
+        R = random_rotations(64, r)
+        raw = (np.einsum("bij,bkj->bki", R, base) + r.randn(64, 1, 3)).astype(np.float32)
+        outs.append(preprocess_keypoints(torch.from_numpy(raw).to(dev)))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), atol=5e-6)
+    seq = build_product("teleop/allegro_hand_right")
+    x0 = torch.from_numpy(np.tile(seq.joint_limits.mean(1).astype(np.float32), (64, 1))).to(dev)
+    q0 = seq.optimizer.retarget_batch(keypoints=outs[0], last_qpos=x0)
+    q1 = seq.optimizer.retarget_batch(keypoints=outs[1], last_qpos=x0)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(q0.cpu().numpy(), q1.cpu().numpy(), atol=2e-3)
+
+
+def test_preprocess_argument_checks():
+    from dex_retargeting_b200.preprocess import preprocess_keypoints
+
+    dev = torch.device("cuda", 0)
+    with pytest.raises(ValueError):
+        preprocess_keypoints(torch.zeros((4, 20, 3), device=dev))
+    with pytest.raises(ValueError):
+        preprocess_keypoints(torch.zeros((4, 21, 3)))
+    with pytest.raises(ValueError):
+        preprocess_keypoints(torch.zeros((4, 21, 3), device=dev), out=torch.zeros((3, 21, 3), device=dev))
+    bad = torch.zeros((2, 21, 3), device=dev)  # all landmarks coincide: no plane -> NaN, never garbage
+    out = preprocess_keypoints(bad)
+    torch.cuda.synchronize()
+    assert torch.isnan(out[:, 1:]).all()
