@@ -120,7 +120,7 @@ class ClockSampler:
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.05)
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 

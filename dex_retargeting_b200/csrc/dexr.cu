@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction: tells the compiler that the role split below never splits a warp
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const bool by_kp = a.io.keypoints != nullptr;
   const float* g_in = by_kp ? a.io.keypoints : a.io.ref_value;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
 
   constexpr int GPW = 32 / G;
   constexpr int KPL = (3 * DEXR_NUM_KEYPOINTS + G - 1) / G;  // keypoint floats per lane
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int gid = warp * GPW + (lane / G);
   const int groups_per_cta = NW * GPW;
@@ -350,7 +352,9 @@ struct dexr_robot {
   size_t stage_bytes = 0;
 };
 
-template <int G> struct FramesCfg { static constexpr int NCW = (G == 16) ? 15 : 11; };  // consumer warps per CTA
+template <int G> struct FramesCfg {
+  static constexpr int kMaxTile = (G == 16) ? 64 : 32;  // frames per ring stage (shared memory budget)
+};
 constexpr int kSeqNW = 8;       // warps per CTA (sequences kernel)
 constexpr int kMaxTile = 64;
 
@@ -477,7 +481,7 @@ static Dims make_dims(const dexr_table_t& t) {
   return d;
 }
 
-template <int G>
+template <int G, int NCW>
 static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
   const dexr_table_t& t = r->host;
   FrameArgs a{};
@@ -489,7 +493,7 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   a.in_row = io->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
   const int slots = r->num_sms;  // one CTA per SM
   long long per = (B + slots - 1) / slots;
-  int T = (int)std::min<long long>(kMaxTile, std::max<long long>(4, per));
+  int T = (int)std::min<long long>(FramesCfg<G>::kMaxTile, std::max<long long>(4, per));
   T = round_up(T, 4);
   a.T = T;
   a.ntiles = (int)((B + T - 1) / T);
@@ -504,7 +508,6 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   a.bar_off = a.ring_off + 2 * a.stage_bytes;
   a.scratch_off = round_up(a.bar_off + 4 * 8 + 2 * 4, 16);
   constexpr int GPW = 32 / G;
-  constexpr int NCW = FramesCfg<G>::NCW;
   const int smem = a.scratch_off + NCW * GPW * Scratch<G>::kFloats * 4;
   auto kern = dexr_frames_kernel<G, NCW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -529,8 +532,11 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   CUDA_TRY(cudaSetDevice(robot->device));
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  return t.dof <= 16 ? launch_frames<16>(r, params, io, num_frames, stream)
-                     : launch_frames<32>(r, params, io, num_frames, stream);
+  if (t.dof <= 16) return launch_frames<16, 15>(r, params, io, num_frames, stream);
+  // one frame per warp: 16 warps x 128 registers (small spills) or 12 warps x 168 registers
+  static const bool wide = [] { const char* e = getenv("DEXR_G32_WARPS"); return !(e && atoi(e) == 12); }();
+  return wide ? launch_frames<32, 15>(r, params, io, num_frames, stream)
+              : launch_frames<32, 11>(r, params, io, num_frames, stream);
 }
 
 template <int G>

@@ -179,10 +179,10 @@ struct Scratch {
   static constexpr int NP = G;
   static constexpr int kFr = 0;                                 // [MAX_RES][4] target xyz, weight c_k
   static constexpr int kLp = kFr + DEXR_MAX_RES * 4;            // [2][MAX_LINKS][4] link positions
-  static constexpr int kU = kLp + 2 * DEXR_MAX_LINKS * 4;       // union: jbuf[2][3][NP] + at[NP][8]  |  Lrow[NP][NP]
-  static constexpr int kUSize = (NP * NP > 14 * NP) ? NP * NP : 14 * NP;
+  static constexpr int kU = kLp + 2 * DEXR_MAX_LINKS * 4;       // jbuf[2][3][NP] (aliased by the 2 Cholesky row buffers) + at[NP][8]
+  static constexpr int kUSize = 14 * NP;
   static constexpr int kHb = kU + kUSize;                       // [NP][NP]   Hessian backup, column per lane
-  static constexpr int kLcol = kHb + NP * NP;                   // [NP][NP+1] L^T rows, conflict-free column reads
+  static constexpr int kLcol = kHb + NP * NP;                   // [NP][NP+1] L^T rows, conflict-free column reads (also mimic-fold temp)
   static constexpr int kFloats = ((kLcol + NP * (NP + 1) + 3) / 4) * 4;
 };
 
@@ -567,7 +567,7 @@ struct Solver {
         for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
         __syncwarp();
         // row fold through shared memory (runtime loop: keeps the code small; only mimic robots get here)
-        float* hrow = lrow();  // free at this point: jbuf / at are no longer read
+        float* hrow = lcol();  // NP x NP temporary: the transposed-factor area is idle during the Hessian build
         for (int s = 0; s < dof; ++s) {
           float acc = 0.f;
           const int cnt = ST().group_count[s];
@@ -626,44 +626,44 @@ struct Solver {
         float y = -g;
         float myinv = 1.0f;
         bool bad = false;
-        float* Lr = lrow();
+        float* Lr = lrow();   // two NP-float row buffers, alternating per pivot
         float* Lc = lcol();
         __syncwarp();
+        // Cholesky, lane = row, as a ROLLED loop: after pivot k every lane shifts its row one column to the
+        // left (fused into the update FMA), so the pivot column is always register H[0] and the loop body is
+        // the same code for every k -- 16-32x less code than the unrolled form (instruction-cache bound
+        // otherwise), same FMA count thanks to the chunk guard.
+        for (int k = 0; k < dof; ++k) {
+          float hk = H[0];
+          if (k == l) hk = fmaf(lam, D, hk);
+          const float dkk = gshfl<G>(hk, k);
+          bad = bad || !(dkk > 1e-20f);
+          const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
+          const float lik = hk * inv;                       // L[l][k] (meaningful for l >= k)
+          const float yk = gshfl<G>(y, k) * inv;            // forward substitution fused
+          if (l == k) { myinv = inv; y = yk; }
+          if (l > k) y = fmaf(-lik, yk, y);
+          float* row = Lr + (k & 1) * NP;
+          row[(l - k - 1) & (NP - 1)] = lik;                // entry j of the row = L[k+1+j][k]
+          Lc[k * (NP + 1) + l] = lik;                       // transposed copy for the back substitution
+          __syncwarp();
+          const int live = dof - k - 1;                     // columns right of the pivot
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          if (k < dof) {
-            float hk = H[k];
-            if (k == l) hk = fmaf(lam, D, hk);
-            const float dkk = gshfl<G>(hk, k);
-            bad = bad || !(dkk > 1e-20f);
-            const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
-            const float lik = hk * inv;
-            const float yk = gshfl<G>(y, k) * inv;
-            if (l == k) { myinv = inv; y = yk; }
-            if (l > k) y = fmaf(-lik, yk, y);
-            Lr[k * NP + l] = lik;
-            Lc[k * (NP + 1) + l] = lik;
-            __syncwarp();
-#pragma unroll
-            for (int j0 = ((k + 1) / 4) * 4; j0 < NP; j0 += 4) {
-              if (j0 < dof) {
-                const float4 lj = *reinterpret_cast<const float4*>(Lr + k * NP + j0);
-                if (j0 + 0 > k) H[j0 + 0] = fmaf(-lik, lj.x, H[j0 + 0]);
-                if (j0 + 1 > k) H[j0 + 1] = fmaf(-lik, lj.y, H[j0 + 1]);
-                if (j0 + 2 > k) H[j0 + 2] = fmaf(-lik, lj.z, H[j0 + 2]);
-                if (j0 + 3 > k) H[j0 + 3] = fmaf(-lik, lj.w, H[j0 + 3]);
-              }
+          for (int j = 0; j < NP; j += 4) {
+            if (j < live) {
+              const float4 r = *reinterpret_cast<const float4*>(row + j);
+              H[j + 0] = fmaf(-lik, r.x, H[j + 1]);
+              if (j + 2 < NP) H[j + 1] = fmaf(-lik, r.y, H[j + 2]);
+              if (j + 3 < NP) H[j + 2] = fmaf(-lik, r.z, H[j + 3]);
+              if (j + 4 < NP) H[j + 3] = fmaf(-lik, r.w, H[j + 4]);
             }
           }
         }
-        // back substitution: L^T delta = y
-#pragma unroll
-        for (int k = NP - 1; k >= 0; --k) {
-          if (k < dof) {
-            const float xk = gshfl<G>(y * myinv, k);
-            if (l == k) y = xk;
-            if (l < k) y = fmaf(-Lc[l * (NP + 1) + k], xk, y);
-          }
+        // back substitution: L^T delta = y (column oriented, transposed copy read conflict free)
+        for (int k = dof - 1; k >= 0; --k) {
+          const float xk = gshfl<G>(y * myinv, k);
+          if (l == k) y = xk;
+          if (l < k) y = fmaf(-Lc[l * (NP + 1) + k], xk, y);
         }
         bad = gany<G>(bad || !isfinite(y), lane);
         float xn = free_ ? fminf(fmaxf(x + y, lo), hi) : x;
