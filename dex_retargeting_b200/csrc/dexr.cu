@@ -180,9 +180,11 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   const int l = sv.l;
   const bool use_filter = a.prm.lp_alpha >= 0.f && a.prm.lp_alpha <= 1.f;
 
-  for (long long s0 = (long long)blockIdx.x * groups_per_cta; s0 < a.S; s0 += (long long)gridDim.x * groups_per_cta) {
+  // Streams are dealt round-robin over CTAs (stream = blockIdx + gridDim * slot): with few streams every SM gets
+  // one or two warps instead of a few SMs getting eight -- the path is latency bound per stream.
+  for (long long base = 0; base < a.S; base += (long long)gridDim.x * groups_per_cta) {
     // all groups of a warp must walk the time loop together (warp-wide shuffles inside solve)
-    const long long s = s0 + gid;
+    const long long s = base + (long long)gid * gridDim.x + blockIdx.x;
     const bool active = s < a.S;
     const long long sc = active ? s : a.S - 1;
     float last = 0.f, fy = 0.f;
@@ -558,9 +560,9 @@ static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_
   auto kern = dexr_sequences_kernel<G, kSeqNW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   // spread streams over as many SMs as possible: latency bound, one stream per group
-  long long ctas = (S + groups - 1) / groups;
-  int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * 2);
-  if (S < (long long)r->num_sms * groups) grid = (int)std::min<long long>(r->num_sms, std::max<long long>(1, S));
+  // one CTA per SM (up to 2 when there are many streams); fewer CTAs than SMs only when S is tiny
+  long long ctas = (S + GPW - 1) / GPW;  // at least one warp's worth of streams per CTA
+  int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * (S >= (long long)r->num_sms * groups * 2 ? 2 : 1));
   kern<<<grid, kSeqNW * 32, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   r->last = dexr_launch_info_t{grid, kSeqNW * 32, smem, 0, G, kSeqNW, r->last.kernels_launched + 1};

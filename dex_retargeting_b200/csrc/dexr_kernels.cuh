@@ -597,21 +597,27 @@ struct Solver {
       if (recheck && (fmask == last_fmask || ++rechecks >= 3)) done = true;
       recheck = false;
       last_fmask = fmask;
-      float hd = 1.0f;
+      // Frozen variables (active bounds, fixed / mimic lanes) get identity rows and columns.  The common case
+      // -- every lane below dof is a free variable -- skips this pass entirely (warp-uniform branch); lanes
+      // at or above dof have all-zero rows and are never pivots (the factorisation stops at dof).
+      if (gany<32>(l < dof && !free_, lane)) {
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const bool keep = free_ && ((fmask >> i) & 1u);
-        float v = keep ? H[i] : 0.f;
-        if (i == l) { v = free_ ? v + 2.0f * nd : 1.0f; hd = v; }
-        H[i] = v;
+        for (int i = 0; i < NP; ++i) {
+          const bool keep = free_ && ((fmask >> i) & 1u);
+          float v = keep ? H[i] : 0.f;
+          if (i == l && !free_) v = 1.0f;
+          H[i] = v;
+        }
       }
       if (!free_) g = 0.f;
-      const float D = fabsf(hd) + 1e-6f;
-      {
-        float* hbuf = hb();
+      float* hbuf = hb();
 #pragma unroll
-        for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
-      }
+      for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
+      // own diagonal entry (register index = lane id is not addressable: read it back from the column store);
+      // the regulariser 2*norm_delta enters on the diagonal at pivot time together with the damping
+      const float reg2 = free_ ? 2.0f * nd : 0.f;
+      const float hd = free_ ? hbuf[l * NP + l] + reg2 : 1.0f;
+      const float D = fabsf(hd) + 1e-6f;
       // ======================= damped Newton trials ====================================
       bool accepted = done;
       float acc_step = 0.f;
@@ -619,7 +625,6 @@ struct Solver {
       for (int trial = 0; trial < kMaxTrials; ++trial) {
         if (!gany<32>(!accepted, lane)) break;
         if (trial > 0) {
-          const float* hbuf = hb();
 #pragma unroll
           for (int i = 0; i < NP; ++i) H[i] = hbuf[i * NP + l];
         }
@@ -635,7 +640,7 @@ struct Solver {
         // otherwise), same FMA count thanks to the chunk guard.
         for (int k = 0; k < dof; ++k) {
           float hk = H[0];
-          if (k == l) hk = fmaf(lam, D, hk);
+          if (k == l) hk += fmaf(lam, D, reg2);
           const float dkk = gshfl<G>(hk, k);
           bad = bad || !(dkk > 1e-20f);
           const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
