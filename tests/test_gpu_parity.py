@@ -376,3 +376,32 @@ def test_full_batch_properties():
         assert obj.task_error(small[i].astype(np.float64)) < 2e-3  # reachable target, small regulariser pull
         xp, kkt = polish(obj, small[i].astype(np.float64), o.lower, o.upper)
         assert np.abs(xp - small[i]).max() < TOL
+
+
+def test_host_buffer_entry_matches_device_entry():
+    """dexr_solve_frames_host (numpy / pinned host buffers, chunked over two internal streams) returns exactly
+    what the device entry returns, for batches below and above the chunk size, with DexPilot flags in/out."""
+    dev = _dev()
+    for key, B in (("teleop/allegro_hand_right", 20000), ("teleop/leap_hand_right_dexpilot", 9000),
+                   ("offline/inspire_hand_right", 5000)):
+        seq = build_product(key)
+        opt = seq.optimizer
+        o = build_oracle(key)
+        rng = np.random.RandomState(13)
+        refs, fixed, x0, _ = synth_problems(o, 250, rng, init_noise=0.05, target_noise=0.005)
+        reps = (B + 249) // 250
+        refs, x0 = np.tile(refs, (reps, 1, 1))[:B], np.tile(x0, (reps, 1))[:B]
+        res = gpu_solve(opt, refs, None, x0)
+        proj = np.zeros((B, opt._objective_spec().len_proj), dtype=np.uint8) if opt.retargeting_type == "DEXPILOT" else None
+        out = opt.retarget_batch_host(ref_value=refs, last_qpos=x0, projected=proj)
+        np.testing.assert_array_equal(out, res["q"])
+        if proj is not None:
+            np.testing.assert_array_equal(proj, res["projected"])
+        # pinned torch CPU tensors are accepted as well
+        pin_ref, pin_x0 = torch.from_numpy(refs).pin_memory(), torch.from_numpy(x0).pin_memory()
+        out2 = torch.empty((B, opt.opt_dof), dtype=torch.float32).pin_memory()
+        proj2 = torch.zeros_like(torch.from_numpy(proj)).pin_memory() if proj is not None else None
+        opt.retarget_batch_host(ref_value=pin_ref, last_qpos=pin_x0, out=out2, projected=proj2)
+        np.testing.assert_array_equal(out2.numpy(), res["q"])
+    with pytest.raises(ValueError):
+        opt.retarget_batch_host(ref_value=refs[:10], last_qpos=x0[:9])
