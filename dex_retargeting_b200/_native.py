@@ -11,6 +11,7 @@ import os
 from pathlib import Path
 
 MAX_LANES, MAX_LINKS, MAX_RES, MAX_GROUP, NUM_KEYPOINTS = 32, 16, 16, 4, 21
+MAX_LINKS_PER_LANE = 4
 LOSS_POSITION, LOSS_VECTOR, LOSS_DEXPILOT = 0, 1, 2
 TABLE_MAGIC = 0x31525844
 

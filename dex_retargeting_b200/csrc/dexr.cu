@@ -382,6 +382,12 @@ static int validate_table(const dexr_table_t* t) {
   }
   for (int k = 0; k < t->n_links; ++k)
     if (t->link_parent[k] >= t->dof) return fail(DEXR_E_INVALID, "robot table: link %d parent out of range", k);
+  for (int c = 0; c < t->dof; ++c) {
+    int n = 0;
+    for (int k = 0; k < t->n_links; ++k) n += (t->link_parent[k] == c);
+    if (n > DEXR_MAX_LINKS_PER_LANE)
+      return fail(DEXR_E_INVALID, "robot table: %d objective links ride on joint %d (max %d)", n, c, DEXR_MAX_LINKS_PER_LANE);
+  }
   return 0;
 }
 

@@ -130,6 +130,9 @@ struct SharedTable {
   // per lane, element i of the 3x3 joint placement: (R0[i], RA[i], RB[i], w) with w = p0[i] (i<3), d0[i-3]
   // (3<=i<6), axis[i-6] (6<=i<9); [i][lane] so that a group's LDS.128 is conflict free
   float4 lane_c[9][DEXR_MAX_LANES];
+  // links riding on each lane: (offset xyz, slot as int bits; slot -1 = none), `own_rounds` entries per lane
+  float4 lane_link[DEXR_MAX_LINKS_PER_LANE][DEXR_MAX_LANES];
+  int own_rounds;
   float clip_lo[DEXR_MAX_LANES], clip_hi[DEXR_MAX_LANES];
   int fixed_index[DEXR_MAX_LANES];
   float4 link_off[DEXR_MAX_LINKS];  // xyz, w = parent lane as int bits
@@ -156,6 +159,11 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
     st.s2_task[i] = tb->s2_task[i];
   }
   for (int i = threadIdx.x; i < DEXR_MAX_LANES; i += blockDim.x) {
+    int cnt = 0;
+    for (int k = 0; k < tb->n_links; ++k)
+      if (tb->link_parent[k] == i && cnt < DEXR_MAX_LINKS_PER_LANE)
+        st.lane_link[cnt++][i] = make_float4(tb->link_off[k][0], tb->link_off[k][1], tb->link_off[k][2], __int_as_float(k));
+    for (int k = cnt; k < DEXR_MAX_LINKS_PER_LANE; ++k) st.lane_link[k][i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     for (int e = 0; e < 9; ++e) {
       const float w = e < 3 ? tb->p0[i][e] : (e < 6 ? tb->d0[i][e - 3] : tb->axis[i][e - 6]);
       st.lane_c[e][i] = make_float4(tb->R0[i][e], tb->RA[i][e], tb->RB[i][e], w);
@@ -164,6 +172,15 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
     st.clip_hi[i] = tb->clip_hi[i];
     st.fixed_index[i] = tb->fixed_index[i];
     st.group_count[i] = tb->group_count[i];
+    if (i == 0) {  // most links any single lane carries (1 for every shipped hand)
+      int mx = 0;
+      for (int c = 0; c < DEXR_MAX_LANES; ++c) {
+        int n = 0;
+        for (int k = 0; k < tb->n_links; ++k) n += (tb->link_parent[k] == c);
+        mx = n > mx ? n : mx;
+      }
+      st.own_rounds = mx > DEXR_MAX_LINKS_PER_LANE ? DEXR_MAX_LINKS_PER_LANE : mx;
+    }
     for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
       st.group_lane[i][f] = tb->group_lane[i][f];
       st.group_mult[i][f] = tb->group_mult[i][f];
@@ -290,19 +307,27 @@ struct Solver {
     }
   }
 
-  // Link origins (robot_wrapper.py:85-87 [updateFramePlacement]) -> shared buffer b.
+  // Link origins (robot_wrapper.py:85-87 [updateFramePlacement]) -> shared buffer b.  Each lane places the links
+  // that ride on its joint (normally one); links fixed to the world are written once per frame (prelude).
   __device__ __forceinline__ void write_links(const float* Rw, const float* pw, int b) const {
     float4* out = lp(b);
+    const int rounds = ST().own_rounds;
+    for (int r = 0; r < rounds; ++r) {
+      const float4 o = ST().lane_link[r][l];
+      const int slot = __float_as_int(o.w);
+      if (slot >= 0)
+        out[slot] = make_float4(fmaf(Rw[0], o.x, fmaf(Rw[1], o.y, fmaf(Rw[2], o.z, pw[0]))),
+                                fmaf(Rw[3], o.x, fmaf(Rw[4], o.y, fmaf(Rw[5], o.z, pw[1]))),
+                                fmaf(Rw[6], o.x, fmaf(Rw[7], o.y, fmaf(Rw[8], o.z, pw[2]))), 0.f);
+    }
+  }
+  __device__ __forceinline__ void write_world_links() const {
     const int L = dm.n_links;
-    for (int k = 0; k < L; ++k) {
+    for (int k = l; k < L; k += G) {
       const float4 o = ST().link_off[k];
-      const int par = __float_as_int(o.w);
-      if (par == l) {
-        out[k] = make_float4(fmaf(Rw[0], o.x, fmaf(Rw[1], o.y, fmaf(Rw[2], o.z, pw[0]))),
-                             fmaf(Rw[3], o.x, fmaf(Rw[4], o.y, fmaf(Rw[5], o.z, pw[1]))),
-                             fmaf(Rw[6], o.x, fmaf(Rw[7], o.y, fmaf(Rw[8], o.z, pw[2]))), 0.f);
-      } else if (par < 0 && l == 0) {
-        out[k] = make_float4(o.x, o.y, o.z, 0.f);
+      if (__float_as_int(o.w) < 0) {
+        lp(0)[k] = make_float4(o.x, o.y, o.z, 0.f);
+        lp(1)[k] = make_float4(o.x, o.y, o.z, 0.f);
       }
     }
   }
@@ -423,6 +448,7 @@ struct Solver {
     q = compose_q(x);
     fk(q, R, p);
     cur = 0;
+    write_world_links();
     write_links(R, p, cur);
     __syncwarp();
     F = cost(cur, x);
@@ -671,6 +697,10 @@ struct Solver {
           if (l < k) y = fmaf(-Lc[l * (NP + 1) + k], xk, y);
         }
         bad = gany<G>(bad || !isfinite(y), lane);
+        if (!gany<32>(!accepted && !bad, lane)) {  // indefinite for every pending group: more damping, no FK needed
+          if (!accepted) { lam *= kLamUp; ++rejects; }
+          continue;
+        }
         float xn = free_ ? fminf(fmaxf(x + y, lo), hi) : x;
         if (bad) xn = x;
         const float dx = xn - x;

@@ -184,6 +184,12 @@ def compile_table(
             t.link_off[k][e] = model.link_p[li][e]
         t.link_anc_mask[k] = t.anc_mask[par] if par >= 0 else 0
 
+    for c in range(dof):
+        riders = [objective.link_names[k] for k in range(L) if t.link_parent[k] == c]
+        if len(riders) > N.MAX_LINKS_PER_LANE:
+            raise ValueError(f"{len(riders)} objective links ({riders}) are attached to joint {names[c]}; "
+                             f"at most {N.MAX_LINKS_PER_LANE} per joint are supported")
+
     m = len(objective.res_task)
     if not 1 <= m <= N.MAX_RES:
         raise ValueError(f"objective has {m} residual blocks; supported 1..{N.MAX_RES}")

@@ -31,6 +31,7 @@ extern "C" {
 #define DEXR_MAX_LINKS 16  /* links whose position enters the objective                             */
 #define DEXR_MAX_RES 16    /* residual blocks: vectors (vector / dexpilot) or points (position)     */
 #define DEXR_MAX_GROUP 4   /* joints driven by one optimisation variable (itself + mimic joints)    */
+#define DEXR_MAX_LINKS_PER_LANE 4 /* objective links rigidly attached to the same movable joint        */
 #define DEXR_NUM_KEYPOINTS 21
 #define DEXR_NO_INDEX (-1)
 

@@ -42,6 +42,7 @@ def test_header_constants_match_binding():
     assert int(consts["DEXR_MAX_LINKS"]) == N.MAX_LINKS
     assert int(consts["DEXR_MAX_RES"]) == N.MAX_RES
     assert int(consts["DEXR_MAX_GROUP"]) == N.MAX_GROUP
+    assert int(consts["DEXR_MAX_LINKS_PER_LANE"]) == N.MAX_LINKS_PER_LANE
     assert int(consts["DEXR_NUM_KEYPOINTS"]) == N.NUM_KEYPOINTS
     assert (int(consts["DEXR_LOSS_POSITION"]), int(consts["DEXR_LOSS_VECTOR"]), int(consts["DEXR_LOSS_DEXPILOT"])) == (0, 1, 2)
 
