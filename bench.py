@@ -342,7 +342,9 @@ def main():
                          "note": "latency/FP32-issue bound solver: see DESIGN.md for the instruction-level roofline"},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * (252 + 64),
                     "d2h_bytes_per_step": B * 64, "ms_per_step": e2e_ms, "steps": e2e_steps, "checksum": checksum,
-                    "api": "Optimizer.retarget_batch_host -> dexr_solve_frames_host (pinned host in/out)"},
+                    "api": "Optimizer.retarget_batch_host -> dexr_solve_frames_host, pinned host buffers in and out; zero-copy: the "
+                           "kernel's TMA producer pulls the input tiles from host memory over PCIe and the results are "
+                           "stored straight to host memory, all inside the timed region"},
             "gpu_launches": args.steps, "clocks": clk.summary(),
             "solver": {"mean_iterations": iters_mean, "frames_flagged": flagged, "launch": opt.engine().launch_info()},
         }

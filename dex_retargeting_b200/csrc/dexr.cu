@@ -631,11 +631,45 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
   if (t.n_fixed > 0 && !h->fixed_qpos) return fail(DEXR_E_INVALID, "fixed_qpos is NULL");
   CUDA_TRY(cudaSetDevice(robot->device));
   const int in_row = h->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
+  if (!robot->streams[0]) CUDA_TRY(cudaStreamCreateWithFlags(&robot->streams[0], cudaStreamNonBlocking));
+  // Zero-copy fast path: when every buffer is page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g.
+  // torch pin_memory()), the kernel reads and writes it directly -- the producer warp's bulk copies pull the
+  // input tiles over PCIe straight into shared memory while the consumers compute, results go back with
+  // 64-byte stores: one launch, no staging buffers, copy fully overlapped with the solve.
+  // (DexPilot flags are read-modify-written byte-wise: that case keeps the staged path.)
+  static const bool zero_copy = [] { const char* e = getenv("DEXR_HOST_ZEROCOPY"); return !(e && atoi(e) == 0); }();
+  if (zero_copy && !h->projected) {
+    bool ok = true;
+    dexr_frames_t d = *h;
+    auto map = [&](const void* host, const void** dev) {
+      if (!host) { *dev = nullptr; return; }
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); ok = false; return; }
+      if (a.type != cudaMemoryTypeHost || !a.devicePointer) { ok = false; return; }
+      *dev = a.devicePointer;
+    };
+    map(h->keypoints, (const void**)&d.keypoints);
+    map(h->ref_value, (const void**)&d.ref_value);
+    map(h->fixed_qpos, (const void**)&d.fixed_qpos);
+    map(h->last_qpos, (const void**)&d.last_qpos);
+    map(h->qpos_out, (const void**)&d.qpos_out);
+    map(h->robot_qpos_out, (const void**)&d.robot_qpos_out);
+    map(h->status_out, (const void**)&d.status_out);
+    map(h->cost_out, (const void**)&d.cost_out);
+    if (ok) {
+      if (int e = dexr_solve_frames(robot, params, &d, B, robot->streams[0])) return e;
+      CUDA_TRY(cudaStreamSynchronize(robot->streams[0]));
+      return 0;
+    }
+  }
   // per-frame device bytes, every sub-array padded so that chunk bases stay 16-byte aligned
   const size_t row_in = in_row * 4, row_last = t.n_var * 4, row_fixed = t.n_fixed * 4, row_proj = t.len_proj,
                row_q = t.n_var * 4, row_rq = h->robot_qpos_out ? t.dof * 4 : 0, row_st = h->status_out ? 4 : 0,
                row_c = h->cost_out ? 4 : 0;
-  const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, round_up((int)std::min<int64_t>((B + 3) / 4, 1 << 20), 64)));
+  // chunks per call: enough to overlap copies with the solve, few enough that each launch still fills the GPU
+  static const int n_chunks_env = [] { const char* e = getenv("DEXR_HOST_CHUNKS"); return e ? std::max(1, atoi(e)) : 0; }();
+  const int n_chunks = n_chunks_env ? n_chunks_env : 4;
+  const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, round_up((int)std::min<int64_t>((B + n_chunks - 1) / n_chunks, 1 << 20), 64)));
   auto pad = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t need = pad(chunk * row_in) + pad(chunk * row_last) + pad(chunk * row_fixed) + pad(chunk * row_proj) +
                       pad(chunk * row_q) + pad(chunk * row_rq) + pad(chunk * row_st) + pad(chunk * row_c);

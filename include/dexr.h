@@ -187,9 +187,12 @@ int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t* params, co
 /* Streams: replaces S x T calls of SeqRetargeting.retarget() (seq_retarget.py:112-134). */
 int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params_t* params, const dexr_sequences_t* io,
                          int64_t num_streams, int64_t num_steps, void* cuda_stream);
-/* Same as dexr_solve_frames but every pointer in `io` is a HOST pointer (pinned for best speed):
- * the library stages chunks through its own device buffers, overlapping H2D, solve and D2H on
- * internal streams, and returns when the results are in the host buffers. */
+/* Same as dexr_solve_frames but every pointer in `io` is a HOST pointer; returns when the results are in
+ * the host buffers.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) take the
+ * zero-copy path: one launch whose producer warps bulk-copy the input tiles from host memory over PCIe
+ * into shared memory while the consumers solve, results stored directly to host memory.  Pageable
+ * buffers (and DexPilot flag buffers) are staged in chunks through library-owned device buffers on two
+ * internal streams. */
 int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, const dexr_frames_t* io_host,
                            int64_t num_frames);
 /* Keypoint pre-processing, the step right before the hot path in the reference's teleoperation pipeline

@@ -108,6 +108,7 @@ class ProtoProblem:
 NOISE = 2e-6
 RFAR = 0.2
 LDOWN = 0.1
+LAMFAST = 1e-3
 KEEP_LAM_ON_NOISE = True
 LUP = 10.0
 STATS = {'solves': 0}
@@ -118,7 +119,8 @@ def huber(d, beta):
 
 
 def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, tol=1e-6, ggn=True, lam0=1e-3,
-                verbose=False, newton=False, hybrid=False, near=0.1, curv_far=True, pos_majorise=False, start_exact=False):
+                verbose=False, newton=False, hybrid=False, near=0.1, curv_far=True, pos_majorise=False, start_exact=False,
+                chord=0.0, extrap=False):
     """target [B,m,3] (already scaled / projected), weights [B,m] or None (position)."""
     o, dt = P.o, P.dt
     B, n = x0.shape
@@ -144,12 +146,17 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
         return L + nd * ((x - last) ** 2).sum(1)
 
     lam = np.full(B, lam0, dt)
+    Afac = np.tile(np.eye(n, dtype=np.float64), (B, 1, 1))
+    fac_act = np.zeros((B, n), bool)
+    use_chord = np.zeros(B, bool)
+    STATS['full'] = STATS.get('full', 0); STATS['chord'] = STATS.get('chord', 0)
     exact = (np.ones(B, bool) if start_exact else np.zeros(B, bool)) if hybrid else np.full(B, ggn)
     done = np.zeros(B, bool)
     iters = np.zeros(B, int)
     pos, J = P.fk(x, fixed)
     r = residuals(pos)
     F = cost(r, x)
+    x_before_last = x.copy()
     for it in range(max_iter):
         x_prev = x.copy()
         # gradient / GGN Hessian at x
@@ -196,8 +203,33 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
         H_f = H * (~act)[:, :, None] * (~act)[:, None, :]
         H_f[:, np.arange(n), np.arange(n)] += act.astype(dt)
         diag = np.abs(H_f[:, np.arange(n), np.arange(n)]) + dt(1e-6)
+        # chord (frozen factor) iteration for frames flagged by the previous step, if the active set is unchanged
+        chord_now = use_chord & ~done & (act == fac_act).all(1)
+        STATS['chord'] += int(chord_now.sum()); STATS['full'] += int((~chord_now & ~done).sum())
+        use_chord = np.zeros(B, bool)
+        chord_ok = np.zeros(B, bool)
+        if chord_now.any():
+            delta = -np.linalg.solve(Afac, g_f.astype(np.float64)[..., None])[..., 0].astype(dt)
+            xn = np.clip(x + delta, lo, hi)
+            posn, Jn = P.fk(xn, fixed)
+            rn = residuals(posn)
+            Fn = cost(rn, xn)
+            step = np.abs(xn - x).max(1)
+            noise = dt(NOISE) * np.abs(F)
+            prev_step = np.abs(x - x_before_last).max(1)
+            okc = chord_now & ((Fn <= F + noise) | (step < tol)) & (step < 0.5 * prev_step)
+            chord_ok = okc
+            x_before_last = np.where(okc[:, None], x, x_before_last)
+            x = np.where(okc[:, None], xn, x)
+            pos = np.where(okc[:, None, None], posn, pos)
+            J = np.where(okc[:, None, None, None], Jn, J)
+            r = np.where(okc[:, None, None], rn, r)
+            F = np.where(okc, Fn, F)
+            done |= okc & (step < tol)
+            use_chord = okc & ~done
+            iters += chord_now.astype(int)
         # inner loop: try lambdas
-        accepted = done.copy()
+        accepted = done.copy() | chord_now   # chord frames skip the full solve this iteration (failed ones retry fully next time)
         switch = np.zeros(B, bool)
         for trial in range(8):
             STATS['solves'] += int((~accepted).sum())
@@ -225,15 +257,26 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             J = np.where(upd[:, None, None, None], Jn, J)
             r = np.where(upd[:, None, None], rn, r) if r.ndim == 3 else r
             F = np.where(upd, Fn, F)
-            newly_done = upd & (step < tol)
+            pstep = np.abs(x_prev - x_before_last).max(1)
+            unclipped = (np.abs((x + delta) - xn).max(1) == 0)
+            fast = extrap & (pstep > 0) & (step < 0.1 * pstep) & (step * step / np.maximum(pstep, 1e-30) < tol) & (step < 1e-3) & (lam <= dt(LAMFAST)) & unclipped & (trial == 0) & exact & (Fn <= F)
+            newly_done = upd & ((step < tol) | fast)
             iters += (~done).astype(int) * (0 if trial else 1)
             done |= newly_done
             verified = Fn < F_before - noise if KEEP_LAM_ON_NOISE else np.ones(B, bool)
             lam = np.where(upd & verified, np.maximum(lam * dt(LDOWN), dt(1e-7)), np.where(accepted | upd, lam, lam * dt(LUP)))
+            # remember the factor of accepted steps; request a chord iteration after small exact steps
+            if extrap and not chord > 0:
+                x_before_last = np.where(upd[:, None], x_prev, x_before_last)
+            if chord > 0:
+                Afac = np.where(upd[:, None, None], A.astype(np.float64), Afac)
+                fac_act = np.where(upd[:, None], act, fac_act)
+                x_before_last = np.where(upd[:, None], x_prev, x_before_last)
+                use_chord = np.where(upd, (step < chord) & exact & ~newly_done, use_chord)
             accepted |= upd
             if accepted.all():
                 break
-        stuck = ~accepted
+        stuck = ~accepted & ~chord_now
         if hybrid:
             done |= stuck & ~exact  # the majoriser model failed too: at the (numerical) minimum
             laststep = np.abs(x - x_prev).max(1)
