@@ -405,3 +405,31 @@ def test_host_buffer_entry_matches_device_entry():
         np.testing.assert_array_equal(out2.numpy(), res["q"])
     with pytest.raises(ValueError):
         opt.retarget_batch_host(ref_value=refs[:10], last_qpos=x0[:9])
+
+
+def test_maximum_size_robot_parity(tmp_path):
+    """32-joint single chain (all 32 lanes, 5 pointer-jumping rounds, prismatic joints mixed in), position loss."""
+    from synthetic_robots import write_chain
+    from dex_retargeting_b200.retargeting_config import RetargetingConfig
+    from oracle.objectives import OracleOptimizer
+
+    p, cfg = write_chain(tmp_path, 32, prismatic_every=5)
+    seq = RetargetingConfig.from_dict(dict(cfg)).build()
+    o = OracleOptimizer(dict(cfg), str(tmp_path))
+    assert o.robot.dof_joint_names == seq.optimizer.robot.dof_joint_names
+    rng = np.random.RandomState(2)
+    refs, fixed, x0, _ = synth_problems(o, 16, rng, init_noise=0.05, target_noise=0.005)
+    XB, FB = oracle_b(o, refs, fixed, x0)
+    res = gpu_solve(seq.optimizer, refs, fixed, x0)
+    dq = check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.85)
+    assert np.median(dq) < 2e-5
+
+
+def test_empty_batch_is_a_no_op():
+    seq = build_product("teleop/allegro_hand_right")
+    opt = seq.optimizer
+    dev = _dev()
+    q = opt.retarget_batch(torch.zeros((0, 4, 3), device=dev), None, torch.zeros((0, 16), device=dev))
+    assert tuple(q.shape) == (0, 16)
+    out = opt.retarget_batch_host(ref_value=np.zeros((0, 4, 3), np.float32), last_qpos=np.zeros((0, 16), np.float32))
+    assert out.shape == (0, 16)

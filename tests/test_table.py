@@ -148,3 +148,27 @@ def test_table_compiler_errors():
     bad = ObjectiveSpec(spec.loss, spec.link_names, spec.res_task, spec.res_origin, [25] * 4, spec.res_human_origin)
     with pytest.raises(ValueError):
         compile_table(kin, opt.target_joint_names, bad, seq.joint_limits)
+
+
+def test_maximum_size_robot_32_joints_deep_chain(tmp_path):
+    """32 movable joints in ONE chain: the lane budget (32) and the pointer-jumping depth (5 rounds) at their
+    limits; one more joint must be refused."""
+    from synthetic_robots import write_chain
+    from dex_retargeting_b200.retargeting_config import RetargetingConfig
+
+    p, cfg = write_chain(tmp_path, 32, prismatic_every=5)
+    seq = RetargetingConfig.from_dict(cfg).build()
+    opt = seq.optimizer
+    t = opt.build_table()
+    assert (t.dof, t.n_var, t.n_rounds, t.n_links, t.n_res) == (32, 32, 5, 4, 4)
+    kin = opt.robot.kin
+    assert kin.joint_depth.max() == 32
+    rng = np.random.RandomState(0)
+    q = rng.uniform(kin.joint_limits[:, 0], kin.joint_limits[:, 1])
+    R, pp = emulate_table_fk(t, q)
+    Rw, pw = kin.forward_kinematics(q)
+    np.testing.assert_allclose(R, Rw, atol=5e-6)
+    np.testing.assert_allclose(pp, pw, atol=5e-6)
+    p33, cfg33 = write_chain(tmp_path, 33)
+    with pytest.raises(ValueError, match="at most 32"):
+        RetargetingConfig.from_dict(cfg33).build().optimizer.build_table()
