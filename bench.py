@@ -93,36 +93,46 @@ def workload(seq):
 
 # --------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    def __init__(self, index):
-        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
-        self.max_mhz = None
-        self._t = threading.Thread(target=self._run, daemon=True)
+    """SM clock + throttle reasons sampled DURING the timed region (NVML): a background thread polls every
+    2 ms, and the main thread adds one sample right after the launches are enqueued (GPU still busy), so even
+    a timed region of a few milliseconds is covered."""
 
-    def _run(self):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.max_mhz, self._h, self._nv = None, None, None
         try:
             import pynvml
 
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            names = {
-                getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-            }
-            while not self._stop.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                try:
-                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.002)
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def sample_now(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for bit, nm in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample_now()
+            time.sleep(0.002)
 
     def __enter__(self):
         self._t.start()
@@ -292,6 +302,7 @@ def main():
         for s in range(args.steps):
             opt.retarget_batch(keypoints=kp_sets[s % N_INPUT_SETS], last_qpos=x0_sets[s % N_INPUT_SETS], out=out, status_out=status)
             evs[s + 1].record()
+        clk.sample_now()  # launches are enqueued, the GPU is still working through them
         barrier()
     total_ms = evs[0].elapsed_time(evs[-1])
     launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]

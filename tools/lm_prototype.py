@@ -108,6 +108,7 @@ class ProtoProblem:
 NOISE = 2e-6
 RFAR = 0.2
 LDOWN = 0.1
+NO_DEC_AFTER_REJECT = False
 LAMFAST = 1e-3
 KEEP_LAM_ON_NOISE = True
 LUP = 10.0
@@ -264,7 +265,8 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             iters += (~done).astype(int) * (0 if trial else 1)
             done |= newly_done
             verified = Fn < F_before - noise if KEEP_LAM_ON_NOISE else np.ones(B, bool)
-            lam = np.where(upd & verified, np.maximum(lam * dt(LDOWN), dt(1e-7)), np.where(accepted | upd, lam, lam * dt(LUP)))
+            dec_ok = verified & ((trial == 0) | (not NO_DEC_AFTER_REJECT))
+            lam = np.where(upd & dec_ok, np.maximum(lam * dt(LDOWN), dt(1e-7)), np.where(accepted | upd, lam, lam * dt(LUP)))
             # remember the factor of accepted steps; request a chord iteration after small exact steps
             if extrap and not chord > 0:
                 x_before_last = np.where(upd[:, None], x_prev, x_before_last)
