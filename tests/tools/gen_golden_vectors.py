@@ -6,14 +6,14 @@ reference's: mode B (converged minimiser, the joint-space parity target) and mod
 SLSQP) for the same inputs.  They pin the oracle against regressions (tests/test_golden_vectors.py, CPU) and give
 the GPU suite fixed expected outputs that need no CPU solve at test time.
 
-Usage: python tools/gen_golden_vectors.py
+Usage: python tests/tools/gen_golden_vectors.py
 """
 import sys
 from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from helpers import build_oracle, keypoint_trajectory, synth_problems  # noqa: E402
