@@ -46,7 +46,7 @@ struct SeqArgs {
 // ------------------------------------------------------------------------------------------------
 // independent frames: producer warp (TMA ring) + NCW consumer warps
 // ------------------------------------------------------------------------------------------------
-template <int G, int NCW>
+template <int G, int BW, int NCW>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const FrameArgs a) {
   unsigned char* const smem = dsmem;
   SharedTable* st = reinterpret_cast<SharedTable*>(smem);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
   // ===================== consumers: one frame per group of G lanes =========================
   constexpr int GPW = 32 / G;
   const int gid = warp * GPW + (lane / G);
-  Solver<G> sv;
+  Solver<G, BW> sv;
   sv.init(a.table, a.dm, (uint32_t)(a.scratch_off + gid * Scratch<G>::kFloats * 4), a.prm, lane);
 
   int it = 0;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
 // ------------------------------------------------------------------------------------------------
 // sequences: one group owns one stream and walks its T frames (seq_retarget.py:112-134)
 // ------------------------------------------------------------------------------------------------
-template <int G, int NW>
+template <int G, int BW, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArgs a) {
   unsigned char* const smem = dsmem;
   SharedTable* st = reinterpret_cast<SharedTable*>(smem);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   const int groups_per_cta = NW * GPW;
   const uint32_t scratch_off = (uint32_t)(a.scratch_off + gid * (Scratch<G>::kFloats + 64) * 4);
   float* kpbuf = reinterpret_cast<float*>(smem + scratch_off) + Scratch<G>::kFloats;  // 63 floats: current keypoints
-  Solver<G> sv;
+  Solver<G, BW> sv;
   sv.init(a.table, a.dm, scratch_off, a.prm, lane);
   const int l = sv.l;
   const bool use_filter = a.prm.lp_alpha >= 0.f && a.prm.lp_alpha <= 1.f;
@@ -382,6 +382,22 @@ static int validate_table(const dexr_table_t* t) {
   }
   for (int k = 0; k < t->n_links; ++k)
     if (t->link_parent[k] >= t->dof) return fail(DEXR_E_INVALID, "robot table: link %d parent out of range", k);
+  if (t->block_width != 0) {
+    const int bw = t->block_width;
+    if ((bw != 4 && bw != 8) || t->dof % bw != 0 || t->has_mimic || t->n_var != t->dof)
+      return fail(DEXR_E_INVALID, "robot table: block_width %d inconsistent (dof %d, mimic %d)", bw, t->dof, t->has_mimic);
+    for (int c = 0; c < t->dof; ++c) {  // ancestors must stay inside the lane window
+      const uint32_t window = ((bw == 32 ? 0u : (1u << bw)) - 1u) << (c / bw * bw);
+      if (t->anc_mask[c] & ~window) return fail(DEXR_E_INVALID, "robot table: block_width %d but joint %d has ancestors outside its window", bw, c);
+    }
+    for (int k = 0; k < t->n_res; ++k) {
+      uint32_t m = t->link_anc_mask[t->res_task[k]] | (t->res_origin[k] >= 0 ? t->link_anc_mask[t->res_origin[k]] : 0u);
+      if (m) {
+        int first = __builtin_ctz(m) / bw, last = (31 - __builtin_clz(m)) / bw;
+        if (first != last) return fail(DEXR_E_INVALID, "robot table: block_width %d but residual %d couples two windows", bw, k);
+      }
+    }
+  }
   for (int c = 0; c < t->dof; ++c) {
     int n = 0;
     for (int k = 0; k < t->n_links; ++k) n += (t->link_parent[k] == c);
@@ -486,10 +502,11 @@ static Dims make_dims(const dexr_table_t& t) {
   d.dof = t.dof; d.n_var = t.n_var; d.n_fixed = t.n_fixed; d.n_links = t.n_links; d.n_res = t.n_res; d.loss = t.loss;
   d.n_rounds = t.n_rounds; d.has_mimic = t.has_mimic; d.num_fingers = t.num_fingers; d.len_proj = t.len_proj;
   d.len_s1 = t.len_s1;
+  d.block_width = t.block_width;
   return d;
 }
 
-template <int G, int NCW>
+template <int G, int BW, int NCW>
 static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
   const dexr_table_t& t = r->host;
   FrameArgs a{};
@@ -517,7 +534,7 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   a.scratch_off = round_up(a.bar_off + 4 * 8 + 2 * 4, 16);
   constexpr int GPW = 32 / G;
   const int smem = a.scratch_off + NCW * GPW * Scratch<G>::kFloats * 4;
-  auto kern = dexr_frames_kernel<G, NCW>;
+  auto kern = dexr_frames_kernel<G, BW, NCW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(a.ntiles, slots);
   kern<<<grid, (NCW + 1) * 32, smem, stream>>>(a);
@@ -540,14 +557,18 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   CUDA_TRY(cudaSetDevice(robot->device));
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  if (t.dof <= 16) return launch_frames<16, 15>(r, params, io, num_frames, stream);
+  if (t.dof <= 16) {
+    // decoupled 4-joint fingers (Allegro / LEAP vector retargeting): block-diagonal Newton system
+    if (t.block_width == 4) return launch_frames<16, 4, 15>(r, params, io, num_frames, stream);
+    return launch_frames<16, 0, 15>(r, params, io, num_frames, stream);
+  }
   // one frame per warp: 16 warps x 128 registers (small spills) or 12 warps x 168 registers
   static const bool wide = [] { const char* e = getenv("DEXR_G32_WARPS"); return !(e && atoi(e) == 12); }();
-  return wide ? launch_frames<32, 15>(r, params, io, num_frames, stream)
-              : launch_frames<32, 11>(r, params, io, num_frames, stream);
+  return wide ? launch_frames<32, 0, 15>(r, params, io, num_frames, stream)
+              : launch_frames<32, 0, 11>(r, params, io, num_frames, stream);
 }
 
-template <int G>
+template <int G, int BW>
 static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_sequences_t* io, long long S, int steps,
                             cudaStream_t stream) {
   const dexr_table_t& t = r->host;
@@ -563,7 +584,7 @@ static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_
   constexpr int GPW = 32 / G;
   const int groups = kSeqNW * GPW;
   const int smem = a.scratch_off + groups * (Scratch<G>::kFloats + 64) * 4;
-  auto kern = dexr_sequences_kernel<G, kSeqNW>;
+  auto kern = dexr_sequences_kernel<G, BW, kSeqNW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   // spread streams over as many SMs as possible: latency bound, one stream per group
   // one CTA per SM (up to 2 when there are many streams); fewer CTAs than SMs only when S is tiny
@@ -589,8 +610,11 @@ extern "C" int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params
   CUDA_TRY(cudaSetDevice(robot->device));
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  return t.dof <= 16 ? launch_sequences<16>(r, params, io, num_streams, (int)num_steps, stream)
-                     : launch_sequences<32>(r, params, io, num_streams, (int)num_steps, stream);
+  if (t.dof <= 16) {
+    if (t.block_width == 4) return launch_sequences<16, 4>(r, params, io, num_streams, (int)num_steps, stream);
+    return launch_sequences<16, 0>(r, params, io, num_streams, (int)num_steps, stream);
+  }
+  return launch_sequences<32, 0>(r, params, io, num_streams, (int)num_steps, stream);
 }
 
 extern "C" {

@@ -121,6 +121,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // depends on them is provably warp-uniform for the compiler (no divergence scaffolding around shuffles).
 struct Dims {
   int dof, n_var, n_fixed, n_links, n_res, loss, n_rounds, has_mimic, num_fingers, len_proj, len_s1;
+  int block_width;  // 0 = dense Hessian; 4 / 8 = the Hessian is block diagonal over aligned lane windows of this width
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -214,9 +215,11 @@ struct FrameInputs {
   uint8_t* projected;  // len_proj flags (global) or nullptr
 };
 
-template <int G>
+template <int G, int BW = 0>
 struct Solver {
   static constexpr int NP = G;
+  static_assert(BW == 0 || (BW % 4 == 0 && BW < G), "block width must be a multiple of 4 below the group width");
+  static constexpr int HN = (BW == 0) ? G : BW;  // Hessian row segment held per lane
   using SC = Scratch<G>;
 
   // ---- lane constants kept in registers (the 3x4 joint placement lives in shared memory) ----
@@ -468,9 +471,9 @@ struct Solver {
 
     while (gany<32>(!done, lane)) {
       // ======================= gradient + exact Hessian at x ===========================
-      float H[NP];
+      float H[HN];
 #pragma unroll
-      for (int i = 0; i < NP; ++i) H[i] = 0.f;
+      for (int i = 0; i < HN; ++i) H[i] = 0.f;
       float g = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
       {
         const float ax0 = ST().lane_c[6][l].w, ax1 = ST().lane_c[7][l].w, ax2 = ST().lane_c[8][l].w;
@@ -481,6 +484,13 @@ struct Solver {
       const bool rev = jtype == 0;
       const int m = dm.n_res;
       const int loss = dm.loss;
+      // Block mode: when the kinematic chains are decoupled (every residual touches one finger and the fingers
+      // share no movable ancestor) the Hessian is block diagonal.  Each lane then keeps only its own block's row
+      // segment -- register H[j] holds column cb + j -- and all blocks are factorised at the same time: bw
+      // pivots instead of dof.  Dense mode is the same code with bw = NP and cb = 0.
+      constexpr bool dense = BW == 0;
+      const int bw = dense ? dof : BW;
+      const int cb = dense ? 0 : (l & ~(BW - 1));
       const float4* lpc = lp(cur);
       float rmax = 0.f;
       for (int k = 0; k < m; ++k) {
@@ -538,11 +548,12 @@ struct Solver {
         __syncwarp();
         const uint32_t cols = mt | mo;
 #pragma unroll
-        for (int blk = 0; blk < NP / 4; ++blk) {
-          if ((cols >> (4 * blk)) & 0xFu) {
-            const float4 c0 = *reinterpret_cast<const float4*>(jbuf(b, 0) + 4 * blk);
-            const float4 c1 = *reinterpret_cast<const float4*>(jbuf(b, 1) + 4 * blk);
-            const float4 c2 = *reinterpret_cast<const float4*>(jbuf(b, 2) + 4 * blk);
+        for (int blk = 0; blk < HN / 4; ++blk) {
+          if (4 * blk < bw && (!dense || ((cols >> (4 * blk)) & 0xFu))) {
+            const int c4 = cb + 4 * blk;  // first of the four columns this chunk accumulates
+            const float4 c0 = *reinterpret_cast<const float4*>(jbuf(b, 0) + c4);
+            const float4 c1 = *reinterpret_cast<const float4*>(jbuf(b, 1) + c4);
+            const float4 c2 = *reinterpret_cast<const float4*>(jbuf(b, 2) + c4);
             H[4 * blk + 0] = fmaf(c0.x, y0, fmaf(c1.x, y1, fmaf(c2.x, y2, H[4 * blk + 0])));
             H[4 * blk + 1] = fmaf(c0.y, y0, fmaf(c1.y, y1, fmaf(c2.y, y2, H[4 * blk + 1])));
             H[4 * blk + 2] = fmaf(c0.z, y0, fmaf(c1.z, y1, fmaf(c2.z, y2, H[4 * blk + 2])));
@@ -558,20 +569,21 @@ struct Solver {
         at()[2 * l + 1] = make_float4(t0, t1, t2, 0.f);
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          if (i < dof) {
+        for (int j = 0; j < HN; ++j) {
+          if (j < bw) {
+            const int i = cb + j;  // the joint this register column stands for
             const float4 ai = at()[2 * i];
             const float4 ti_ = at()[2 * i + 1];
             const bool up = (anc >> i) & 1u;
             const bool dn = (desc >> i) & 1u;
             const float vu = fmaf(ai.x, t0, fmaf(ai.y, t1, ai.z * t2));
             const float vd = fmaf(ar0, ti_.x, fmaf(ar1, ti_.y, ar2 * ti_.z));
-            H[i] += curv_on ? (up ? vu : (dn ? vd : 0.f)) : 0.f;
+            H[j] += curv_on ? (up ? vu : (dn ? vd : 0.f)) : 0.f;
           }
         }
       }
       // ---- mimic fold: H_x = M^T H_q M, g_x = M^T g_q (kinematics_adaptor.py:107-113) ----
-      if (dm.has_mimic) {
+      if constexpr (BW == 0) if (dm.has_mimic) {
         const float ml = var >= 0 ? 1.0f : (msrc >= 0 ? mmult : 0.f);
         float* hbuf = hb();
         __syncwarp();
@@ -590,7 +602,7 @@ struct Solver {
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
+        for (int i = 0; i < HN; ++i) hbuf[i * NP + l] = H[i];
         __syncwarp();
         // row fold through shared memory (runtime loop: keeps the code small; only mimic robots get here)
         float* hrow = lcol();  // NP x NP temporary: the transposed-factor area is idle during the Hessian build
@@ -628,21 +640,21 @@ struct Solver {
       // at or above dof have all-zero rows and are never pivots (the factorisation stops at dof).
       if (gany<32>(l < dof && !free_, lane)) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          const bool keep = free_ && ((fmask >> i) & 1u);
-          float v = keep ? H[i] : 0.f;
-          if (i == l && !free_) v = 1.0f;
-          H[i] = v;
+        for (int j = 0; j < HN; ++j) {
+          const bool keep = free_ && ((fmask >> (cb + j)) & 1u);
+          float v = keep ? H[j] : 0.f;
+          if (cb + j == l && !free_) v = 1.0f;
+          H[j] = v;
         }
       }
       if (!free_) g = 0.f;
       float* hbuf = hb();
 #pragma unroll
-      for (int i = 0; i < NP; ++i) hbuf[i * NP + l] = H[i];
+      for (int i = 0; i < HN; ++i) hbuf[i * NP + l] = H[i];
       // own diagonal entry (register index = lane id is not addressable: read it back from the column store);
       // the regulariser 2*norm_delta enters on the diagonal at pivot time together with the damping
       const float reg2 = free_ ? 2.0f * nd : 0.f;
-      const float hd = free_ ? hbuf[l * NP + l] + reg2 : 1.0f;
+      const float hd = free_ ? hbuf[(l - cb) * NP + l] + reg2 : 1.0f;
       const float D = fabsf(hd) + 1e-6f;
       // ======================= damped Newton trials ====================================
       bool accepted = done;
@@ -652,7 +664,7 @@ struct Solver {
         if (!gany<32>(!accepted, lane)) break;
         if (trial > 0) {
 #pragma unroll
-          for (int i = 0; i < NP; ++i) H[i] = hbuf[i * NP + l];
+          for (int i = 0; i < HN; ++i) H[i] = hbuf[i * NP + l];
         }
         float y = -g;
         float myinv = 1.0f;
@@ -664,37 +676,39 @@ struct Solver {
         // left (fused into the update FMA), so the pivot column is always register H[0] and the loop body is
         // the same code for every k -- 16-32x less code than the unrolled form (instruction-cache bound
         // otherwise), same FMA count thanks to the chunk guard.
-        for (int k = 0; k < dof; ++k) {
+        for (int k = 0; k < bw; ++k) {
+          const int pk = cb + k;  // pivot lane (of this lane's block)
           float hk = H[0];
-          if (k == l) hk += fmaf(lam, D, reg2);
-          const float dkk = gshfl<G>(hk, k);
+          if (pk == l) hk += fmaf(lam, D, reg2);
+          const float dkk = gshfl<G>(hk, pk);
           bad = bad || !(dkk > 1e-20f);
           const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
           const float lik = hk * inv;                       // L[l][k] (meaningful for l >= k)
-          const float yk = gshfl<G>(y, k) * inv;            // forward substitution fused
-          if (l == k) { myinv = inv; y = yk; }
-          if (l > k) y = fmaf(-lik, yk, y);
-          float* row = Lr + (k & 1) * NP;
-          row[(l - k - 1) & (NP - 1)] = lik;                // entry j of the row = L[k+1+j][k]
+          const float yk = gshfl<G>(y, pk) * inv;           // forward substitution fused
+          if (l == pk) { myinv = inv; y = yk; }
+          if (l > pk) y = fmaf(-lik, yk, y);
+          float* row = Lr + (k & 1) * NP + cb;
+          row[(l - pk - 1) & (dense ? NP - 1 : BW - 1)] = lik;  // entry j of the row = L[pk+1+j][pk]
           Lc[k * (NP + 1) + l] = lik;                       // transposed copy for the back substitution
           __syncwarp();
-          const int live = dof - k - 1;                     // columns right of the pivot
+          const int live = bw - k - 1;                      // columns right of the pivot (inside the block)
 #pragma unroll
-          for (int j = 0; j < NP; j += 4) {
+          for (int j = 0; j < HN; j += 4) {
             if (j < live) {
               const float4 r = *reinterpret_cast<const float4*>(row + j);
               H[j + 0] = fmaf(-lik, r.x, H[j + 1]);
-              if (j + 2 < NP) H[j + 1] = fmaf(-lik, r.y, H[j + 2]);
-              if (j + 3 < NP) H[j + 2] = fmaf(-lik, r.z, H[j + 3]);
-              if (j + 4 < NP) H[j + 3] = fmaf(-lik, r.w, H[j + 4]);
+              if (j + 2 < HN) H[j + 1] = fmaf(-lik, r.y, H[j + 2]);
+              if (j + 3 < HN) H[j + 2] = fmaf(-lik, r.z, H[j + 3]);
+              if (j + 4 < HN) H[j + 3] = fmaf(-lik, r.w, H[j + 4]);
             }
           }
         }
         // back substitution: L^T delta = y (column oriented, transposed copy read conflict free)
-        for (int k = dof - 1; k >= 0; --k) {
-          const float xk = gshfl<G>(y * myinv, k);
-          if (l == k) y = xk;
-          if (l < k) y = fmaf(-Lc[l * (NP + 1) + k], xk, y);
+        for (int k = bw - 1; k >= 0; --k) {
+          const int pk = cb + k;
+          const float xk = gshfl<G>(y * myinv, pk);
+          if (l == pk) y = xk;
+          if (l < pk) y = fmaf(-Lc[(l - cb) * (NP + 1) + pk], xk, y);
         }
         bad = gany<G>(bad || !isfinite(y), lane);
         if (!gany<32>(!accepted && !bad, lane)) {  // indefinite for every pending group: more damping, no FK needed

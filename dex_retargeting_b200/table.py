@@ -203,11 +203,50 @@ def compile_table(
             t.res_human_task[k], t.res_human_origin[k] = ht, ho
         else:
             t.res_task[k], t.res_origin[k], t.res_human_task[k], t.res_human_origin[k] = 0, -1, 0, -1
+    t.block_width = _block_width(t, dof, n_var, has_mimic)
     t.num_fingers, t.len_proj, t.len_s1 = objective.num_fingers, objective.len_proj, objective.len_s1
     for k in range(N.MAX_RES):
         t.s2_origin[k] = objective.s2_origin[k] if k < len(objective.s2_origin) else 0
         t.s2_task[k] = objective.s2_task[k] if k < len(objective.s2_task) else 0
     return t
+
+
+def _block_width(t: N.DexrTable, dof: int, n_var: int, has_mimic: int) -> int:
+    """Width (4 or 8) of the aligned lane windows over which the Newton system is block diagonal, or 0 (dense).
+
+    Two joints are coupled if one is an ancestor of the other (kinematic curvature, shared Jacobian rows) or if
+    some residual block depends on both.  When every coupled set sits inside one aligned window -- e.g. the four
+    4-joint fingers of Allegro / LEAP with a palm-fixed origin link -- the solver factorises all windows side by
+    side (dexr_kernels.cuh, "block mode")."""
+    if has_mimic or n_var != dof:
+        return 0
+    parent = list(range(dof))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    def union_mask(mask):
+        lanes = [i for i in range(dof) if (mask >> i) & 1]
+        for b in lanes[1:]:
+            parent[find(b)] = find(lanes[0])
+
+    for c in range(dof):
+        union_mask(int(t.anc_mask[c]))
+    for k in range(t.n_res):
+        m = int(t.link_anc_mask[t.res_task[k]])
+        if t.res_origin[k] >= 0:
+            m |= int(t.link_anc_mask[t.res_origin[k]])
+        union_mask(m)
+    comps = {}
+    for c in range(dof):
+        comps.setdefault(find(c), []).append(c)
+    for bw in (4, 8):
+        if dof % bw == 0 and bw < dof and all(min(v) // bw == max(v) // bw for v in comps.values()):
+            return bw
+    return 0
 
 
 def table_bytes(t: N.DexrTable) -> bytes:

@@ -73,7 +73,10 @@ typedef struct dexr_table {
   int32_t num_fingers; /* dexpilot only */
   int32_t len_proj;    /* dexpilot: number of finger-pair vectors (S1 + S2) */
   int32_t len_s1;      /* dexpilot: pairs involving the first finger (thumb) */
-  int32_t reserved[3];
+  int32_t block_width; /* 0: dense Hessian.  4 / 8: the joints split into decoupled groups occupying aligned lane
+                          windows of this width (no residual and no ancestor relation crosses a window), so the
+                          Newton system is block diagonal and all blocks are factorised side by side */
+  int32_t reserved[2];
 
   /* ---- per lane ---- */
   float R0[DEXR_MAX_LANES][9];    /* joint placement rotation in the parent joint frame          */
