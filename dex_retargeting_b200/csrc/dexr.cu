@@ -358,7 +358,6 @@ template <int G> struct FramesCfg {
   static constexpr int kMaxTile = (G == 16) ? 64 : 32;  // frames per ring stage (shared memory budget)
 };
 constexpr int kSeqNW = 8;       // warps per CTA (sequences kernel)
-constexpr int kMaxTile = 64;
 
 static int validate_table(const dexr_table_t* t) {
   if (t->magic != 0x31525844u) return fail(DEXR_E_INVALID, "robot table: bad magic 0x%08x", t->magic);
@@ -409,8 +408,14 @@ static int validate_table(const dexr_table_t* t) {
 
 static int finish_create(dexr_robot* r, dexr_robot_t** out) {
   cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, r->device));
+  cudaError_t ce = cudaGetDeviceProperties(&prop, r->device);
+  if (ce != cudaSuccess) {
+    cudaFree(r->table_dev);
+    delete r;
+    return fail(DEXR_E_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(ce));
+  }
   if (prop.major < 10) {
+    cudaFree(r->table_dev);
     delete r;
     return fail(DEXR_E_NODEVICE, "device %d is sm_%d%d; libdexr is built for sm_100a only", r->device, prop.major, prop.minor);
   }
@@ -449,8 +454,13 @@ int dexr_robot_create(const dexr_table_t* table_host, int device, dexr_robot_t**
   if (!r) return fail(DEXR_E_INVALID, "out of host memory");
   r->device = device;
   r->host = *table_host;
-  CUDA_TRY(cudaMalloc(&r->table_dev, sizeof(dexr_table_t)));
-  CUDA_TRY(cudaMemcpy(r->table_dev, table_host, sizeof(dexr_table_t), cudaMemcpyHostToDevice));
+  cudaError_t ce = cudaMalloc(&r->table_dev, sizeof(dexr_table_t));
+  if (ce == cudaSuccess) ce = cudaMemcpy(r->table_dev, table_host, sizeof(dexr_table_t), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    if (r->table_dev) cudaFree(r->table_dev);
+    delete r;
+    return fail(DEXR_E_CUDA, "uploading the robot table failed: %s", cudaGetErrorString(ce));
+  }
   return finish_create(r, out);
 }
 
@@ -461,9 +471,14 @@ int dexr_robot_create_from_device(const void* table_dev, size_t nbytes, int devi
   dexr_robot* r = new (std::nothrow) dexr_robot();
   if (!r) return fail(DEXR_E_INVALID, "out of host memory");
   r->device = device;
-  CUDA_TRY(cudaMalloc(&r->table_dev, sizeof(dexr_table_t)));
-  CUDA_TRY(cudaMemcpy(r->table_dev, table_dev, sizeof(dexr_table_t), cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(&r->host, r->table_dev, sizeof(dexr_table_t), cudaMemcpyDeviceToHost));
+  cudaError_t ce = cudaMalloc(&r->table_dev, sizeof(dexr_table_t));
+  if (ce == cudaSuccess) ce = cudaMemcpy(r->table_dev, table_dev, sizeof(dexr_table_t), cudaMemcpyDeviceToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(&r->host, r->table_dev, sizeof(dexr_table_t), cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) {
+    if (r->table_dev) cudaFree(r->table_dev);
+    delete r;
+    return fail(DEXR_E_CUDA, "adopting the device robot table failed: %s", cudaGetErrorString(ce));
+  }
   if (int e = validate_table(&r->host)) {
     cudaFree(r->table_dev);
     delete r;

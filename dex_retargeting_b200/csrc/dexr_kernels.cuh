@@ -1,25 +1,31 @@
 // dexr_kernels.cuh -- the fused per-frame retargeting solver for sm_100a.
 //
-// One group of G lanes (G = 16 or 32, so one or two hand-frames per warp) owns one hand-frame.
+// One group of G lanes (G = 16 or 32, so two or one hand-frames per warp) owns one hand-frame.
 // Lane c of the group is movable joint c of the robot in pinocchio DoF order.  Everything the
 // reference does per frame on the CPU through nlopt + pinocchio + torch
 // (optimizer.py:77-102, 146-198, 249-304, 510-575; robot_wrapper.py:82-95;
 // kinematics_adaptor.py:102-113 -- paths relative to /root/reference/src/dex_retargeting) happens here
 // without leaving the SM:
 //   * forward kinematics by pointer jumping over the joint tree (log2(depth) rounds of a 12-float
-//     warp shuffle + 3x4 compose), joint constants resident in registers for the kernel's lifetime;
+//     warp shuffle + 3x4 compose); the 3x4 joint placements live in shared memory (one LDS.128 per
+//     matrix element triple), the small per-lane constants in registers for the kernel's lifetime;
 //   * world-aligned linear Jacobian columns a_c x (p_link - p_c), one column per lane;
 //   * the Position / Vector / DexPilot Huber objective, its exact gradient and its exact Hessian:
 //     sum_k Jv_k^T (d2 loss/dr2) Jv_k  +  FK curvature  a_i . sum_l (J_lj x dF/dp_l)  +  2 norm_delta I,
 //     built by broadcasting Jacobian rows through shared memory;
 //   * a bounded Levenberg-Marquardt / Newton iteration: active-set freeze at the box bounds,
-//     in-register Cholesky (lane = row) with fused forward substitution, shared-memory-transposed
+//     in-register Cholesky (lane = row) written as a ROLLED loop (rows rotate one column per pivot, so
+//     the pivot column is always register 0) with fused forward substitution, shared-memory-transposed
 //     back substitution, noise-aware step acceptance in fp32;
+//   * block mode (template parameter BW): robots whose fingers are kinematically decoupled (Allegro,
+//     LEAP with a palm-fixed origin link) have a block-diagonal Newton system; all blocks are built and
+//     factorised side by side, BW pivots instead of dof;
 //   * DexPilot hysteresis flags, weights and projected targets (optimizer.py:456-508);
 //   * for sequences, SeqRetargeting's clip -> solve -> scatter -> mimic -> low-pass recurrence
 //     (seq_retarget.py:112-134, optimizer_utils.py:7-13) carried in registers across time steps.
-// Inputs of a batch are staged HBM -> shared memory by a producer warp with cp.async.bulk (TMA 1-D)
-// into a two-stage ring guarded by mbarriers; consumer groups claim frames from the ring dynamically.
+// Inputs of a batch are staged HBM (or pinned host memory, zero-copy) -> shared memory by a producer warp
+// with cp.async.bulk (TMA 1-D) into a two-stage ring guarded by mbarriers; consumer warps claim frames
+// from the ring dynamically.
 // No tensor cores: n <= 32 unknowns per frame, the work is FP32 issue / latency bound.
 #pragma once
 
