@@ -35,12 +35,9 @@ def _worker(rank, world, port, tmpdir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         key = "teleop/shadow_hand_right"
-        # rank 1 deliberately builds a different robot first: after the broadcast it must solve with rank 0's table
-        seq = build_product(key if rank == 0 else "teleop/allegro_hand_right", device=rank)
-        if rank != 0:
-            seq = build_product(key, device=rank)
-            seq.optimizer.norm_delta = 123.0  # would change the answer if the local table were used ... params are separate
-            seq.optimizer.norm_delta = 4e-3
+        seq = build_product(key, device=rank)
+        if rank != 0:  # perturb rank 1's local limits: after the broadcast it must solve with rank 0's table
+            seq.optimizer.set_joint_limit(seq.joint_limits * 0.5)
         broadcast_table(seq.optimizer, src=0)
         o = build_oracle(key)
         rng = np.random.RandomState(5)

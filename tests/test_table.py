@@ -172,3 +172,31 @@ def test_maximum_size_robot_32_joints_deep_chain(tmp_path):
     p33, cfg33 = write_chain(tmp_path, 33)
     with pytest.raises(ValueError, match="at most 32"):
         RetargetingConfig.from_dict(cfg33).build().optimizer.build_table()
+
+
+def test_block_width_detection():
+    """Decoupled fingers (palm-fixed origin, no shared movable ancestor) -> block-diagonal Newton system."""
+    expect = {"teleop/allegro_hand_right": 4, "teleop/leap_hand_left": 4,          # 4 fingers x 4 joints, wrist origin
+              "teleop/allegro_hand_right_dexpilot": 0,                              # finger pairs couple the fingers
+              "teleop/shadow_hand_right": 0,                                        # two wrist joints above every finger
+              "offline/allegro_hand_right": 0,                                      # dummy free joints above everything
+              "teleop/ability_hand_right": 0, "teleop/schunk_svh_hand_right": 0}    # mimic joints: dense path
+    for key, bw in expect.items():
+        assert build_product(key).optimizer.build_table().block_width == bw, key
+
+
+def test_library_rejects_inconsistent_block_width():
+    import ctypes as C
+
+    lib = N.load()
+    h = C.c_void_p()
+    t = build_product("teleop/shadow_hand_right").optimizer.build_table()
+    t.block_width = 4  # the wrist joints are ancestors of every finger: not block diagonal
+    assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
+    assert b"block_width" in lib.dexr_last_error()
+    t = build_product("teleop/allegro_hand_right_dexpilot").optimizer.build_table()
+    t.block_width = 4  # pair vectors couple two fingers
+    assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
+    assert b"couples two windows" in lib.dexr_last_error()
+    t.block_width = 5
+    assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
