@@ -103,6 +103,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
         for (int i = lane; i < count * a.in_row; i += 32) s_in[i] = gi[i];
         for (int i = lane; i < count * a.dm.n_var; i += 32) s_last[i] = gl[i];
         for (int i = lane; i < count * a.dm.n_fixed; i += 32) s_fixed[i] = gf[i];
+        __threadfence_block();  // every lane's stores are visible CTA-wide before lane 0 publishes the stage
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
       }
