@@ -172,8 +172,9 @@ def _cpu_worker(args):
 
 
 class CpuReferencePool:
-    """The reference-faithful CPU path (oracle mode A: numpy FK + scipy SLSQP at the reference's ftol, value
-    without / gradient with the regulariser) on `cores` single-threaded worker processes."""
+    """The reference-faithful CPU path (oracle mode A: FK / Jacobians in C like the reference's pinocchio, loss in
+    numpy, scipy SLSQP at the reference's ftol, value without / gradient with the regulariser) on `cores`
+    single-threaded worker processes."""
 
     def __init__(self, cores, kp, x0):
         import multiprocessing as mp
@@ -260,7 +261,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
-                                 "note": "restated reference path (numpy FK + scipy SLSQP at the reference's ftol); "
+                                 "note": "restated reference path (C FK/Jacobian + numpy loss + scipy SLSQP at the reference's ftol); "
                                          "pinocchio/nlopt are not installable offline"},
                 "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)

@@ -5,7 +5,9 @@ import this package.  Nothing under `dex_retargeting_b200/` imports it, and the 
 loudly when the CUDA library is missing instead of falling back to anything here.
 
 What it restates (reference file:line, relative to /root/reference):
-  * oracle/robot.py      robot_wrapper.py:8-95 + the pinocchio calls it wraps (FK, frame placement,
+  * oracle/robot.py      (+ oracle/c/orc.c, the same arithmetic in C for speed, cross-checked in
+                         tests/test_oracle_c.py)
+                         robot_wrapper.py:8-95 + the pinocchio calls it wraps (FK, frame placement,
                          LOCAL frame Jacobian rotated to world axes), retargeting_config.py:167-257
                          (model construction order, dummy joints), kinematics_adaptor.py:46-113
   * oracle/objectives.py optimizer.py:116-200 (position), :203-306 (vector), :309-577 (dexpilot)

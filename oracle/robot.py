@@ -17,11 +17,47 @@ Restates (relative to /root/reference):
   yourdfpy.py:1375-1387, 1631-1643, 1942-1989  origin / axis / dummy joints
 DoF order is pinocchio's [third party]: depth first, children by joint name, fixed joints merged.
 """
+import ctypes as C
 import json
 import math
+import os
+import subprocess
 import xml.etree.ElementTree as ET
+from pathlib import Path
 
 import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIBORC = None
+
+
+def build_c_kinematics(force=False):
+    """gcc oracle/c/orc.c -> oracle/_build/liborc.so (the C restatement of this module's kinematics)."""
+    src, out = _HERE / "c" / "orc.c", _HERE / "_build" / "liborc.so"
+    if force or not out.exists() or out.stat().st_mtime < src.stat().st_mtime:
+        out.parent.mkdir(exist_ok=True)
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", str(out), str(src), "-lm"], check=True)
+    return out
+
+
+def _load_c():
+    """The C library if it can be had (built on demand), else None -> pure Python kinematics."""
+    global _LIBORC
+    if _LIBORC is None:
+        if os.environ.get("ORACLE_PURE_PYTHON") == "1":
+            _LIBORC = False
+        else:
+            try:
+                _LIBORC = C.CDLL(str(build_c_kinematics()))
+            except Exception:
+                _LIBORC = False
+    return _LIBORC or None
+
+
+class _OrcModel(C.Structure):
+    _fields_ = [("n_links", C.c_int), ("n_joints", C.c_int), ("dof", C.c_int), ("parent_link", C.c_void_p),
+                ("child_link", C.c_void_p), ("type", C.c_void_p), ("dof_index", C.c_void_p), ("origin", C.c_void_p),
+                ("axis", C.c_void_p), ("chain_start", C.c_void_p), ("chain_joint", C.c_void_p)]
 
 DUMMY_JOINTS = ["dummy_%s_translation_joint" % a for a in "xyz"] + ["dummy_%s_rotation_joint" % a for a in "xyz"]
 DUMMY_LINKS = ["dummy_%s_translation_link" % a for a in "xyz"] + ["dummy_%s_rotation_link" % a for a in "xyz"]
@@ -63,7 +99,7 @@ def _read_urdf(path):
 
 
 class OracleRobot:
-    def __init__(self, desc, add_dummy_free_joint=False):
+    def __init__(self, desc, add_dummy_free_joint=False, use_c=None):
         if isinstance(desc, (str, bytes)) or hasattr(desc, "__fspath__"):
             p = str(desc)
             if p.endswith(".json"):
@@ -117,6 +153,47 @@ class OracleRobot:
                       if j["type"] != "fixed"}
         self._poses = None
         self._joint_frames = None
+        self._c = None
+        lib = _load_c() if use_c in (None, True) else None
+        if use_c is True and lib is None:
+            raise RuntimeError("oracle C kinematics requested but liborc.so could not be built")
+        if lib is not None:
+            self._init_c(lib)
+
+    # -- C restatement (oracle/c/orc.c): same arithmetic, used for speed ----------------------------
+    def _init_c(self, lib):
+        order, stack = [], [self.root]
+        lidx = {self.root: 0}
+        while stack:  # topological order of joints, links numbered as they are reached
+            link = stack.pop()
+            for j in self._out[link]:
+                lidx[j["child"]] = len(lidx)
+                order.append(j)
+                stack.append(j["child"])
+        jidx = {j["name"]: i for i, j in enumerate(order)}
+        tmap = {"fixed": 0, "revolute": 1, "prismatic": 2}
+        a = dict(
+            parent=np.array([lidx[j["parent"]] for j in order], dtype=np.int32),
+            child=np.array([lidx[j["child"]] for j in order], dtype=np.int32),
+            type=np.array([tmap[j["type"]] for j in order], dtype=np.int32),
+            dofi=np.array([self._dof_index.get(j["name"], -1) for j in order], dtype=np.int32),
+            origin=np.ascontiguousarray([self._T0[j["name"]] for j in order], dtype=np.float64),
+            axis=np.ascontiguousarray([self._axis.get(j["name"], np.zeros(3)) for j in order], dtype=np.float64),
+        )
+        start, flat = [0] * (len(lidx) + 1), []
+        by_cidx = sorted(lidx, key=lidx.get)
+        for k, name in enumerate(by_cidx):
+            flat += [jidx[n] for n in self._chains[name]]
+            start[k + 1] = len(flat)
+        a["cstart"] = np.array(start, dtype=np.int32)
+        a["cjoint"] = np.array(flat if flat else [0], dtype=np.int32)
+        m = _OrcModel(len(lidx), len(order), self.dof, *(a[k].ctypes.data for k in ("parent", "child", "type", "dofi", "origin", "axis", "cstart", "cjoint")))
+        self._c = dict(lib=lib, model=m, arrays=a, lidx=lidx,
+                       poses=np.zeros((len(lidx), 16)), axis_w=np.zeros((len(order), 3)), origin_w=np.zeros((len(order), 3)),
+                       link2c=np.array([lidx[n] for n in self.link_names], dtype=np.int32))
+
+    def _c_ids(self, link_ids):
+        return np.ascontiguousarray(self._c["link2c"][np.asarray(link_ids, dtype=np.int64)], dtype=np.int32)
 
     # -- names ---------------------------------------------------------------------------------
     def get_joint_index(self, name):
@@ -137,8 +214,13 @@ class OracleRobot:
 
     # -- kinematics ----------------------------------------------------------------------------
     def compute_forward_kinematics(self, qpos):
-        qpos = np.asarray(qpos, dtype=np.float64)
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
         assert qpos.shape == (self.dof,)
+        if self._c is not None:
+            c = self._c
+            c["lib"].orc_fk(C.byref(c["model"]), qpos.ctypes.data_as(C.c_void_p), c["poses"].ctypes.data_as(C.c_void_p),
+                            c["axis_w"].ctypes.data_as(C.c_void_p), c["origin_w"].ctypes.data_as(C.c_void_p))
+            return
         poses = {self.root: np.eye(4)}
         frames = {}  # movable joint name -> (world axis, world origin, type, chain of dof indices)
         stack = [self.root]
@@ -161,16 +243,33 @@ class OracleRobot:
         self._poses, self._joint_frames = poses, frames
 
     def get_link_pose(self, link_id):
+        if self._c is not None:
+            return self._c["poses"][self._c["link2c"][link_id]].reshape(4, 4).copy()
         return self._poses[self.link_names[link_id]].copy()
 
     def get_link_pose_inv(self, link_id):
-        return np.linalg.inv(self._poses[self.link_names[link_id]])
+        return np.linalg.inv(self.get_link_pose(link_id))
+
+    def _c_call(self, fn, link_ids, *extra):
+        c = self._c
+        ids = self._c_ids(link_ids)
+        getattr(c["lib"], fn)(C.byref(c["model"]), c["poses"].ctypes.data_as(C.c_void_p), c["axis_w"].ctypes.data_as(C.c_void_p),
+                              c["origin_w"].ctypes.data_as(C.c_void_p), C.c_int(len(ids)), ids.ctypes.data_as(C.c_void_p), *extra)
 
     def link_positions(self, link_ids):
+        if self._c is not None:
+            pos = np.empty((len(link_ids), 3))
+            self._c_call("orc_positions_jacobians", link_ids, pos.ctypes.data_as(C.c_void_p), C.c_void_p(None))
+            return pos
         return np.stack([self._poses[self.link_names[i]][:3, 3] for i in link_ids], axis=0)
 
     def link_jacobians(self, link_ids):
         """(len(link_ids), 3, dof): world-aligned linear Jacobian of each link origin."""
+        if self._c is not None:
+            pos = np.empty((len(link_ids), 3))
+            J = np.empty((len(link_ids), 3, self.dof))
+            self._c_call("orc_positions_jacobians", link_ids, pos.ctypes.data_as(C.c_void_p), J.ctypes.data_as(C.c_void_p))
+            return J
         J = np.zeros((len(link_ids), 3, self.dof))
         for r, lid in enumerate(link_ids):
             name = self.link_names[lid]
@@ -189,6 +288,11 @@ class OracleRobot:
           i revolute, j prismatic: a_i x a_j
           i prismatic            : 0
         (a = world axis, o = world joint origin).  Used by the oracle's Newton polish only."""
+        if self._c is not None:
+            S = np.empty((self.dof, self.dof))
+            g = np.ascontiguousarray(gpos, dtype=np.float64)
+            self._c_call("orc_hessian_contraction", link_ids, g.ctypes.data_as(C.c_void_p), S.ctypes.data_as(C.c_void_p))
+            return S
         S = np.zeros((self.dof, self.dof))
         for r, lid in enumerate(link_ids):
             name = self.link_names[lid]
