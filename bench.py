@@ -368,7 +368,7 @@ def main():
             pool.close()
             line["cpu_baseline"] = {"value": r, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n_s} frames of rank 0's first input batch, oracle mode A "
-                                              f"(numpy FK + scipy SLSQP, reference ftol), {cores} processes"}
+                                              f"(C FK/Jacobian + numpy loss + scipy SLSQP, reference ftol), {cores} processes"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
