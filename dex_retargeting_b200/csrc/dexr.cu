@@ -347,7 +347,8 @@ struct dexr_robot {
   int num_sms = 0;
   dexr_table_t* table_dev = nullptr;
   dexr_table_t host;  // header + small arrays used for validation / sizing
-  dexr_launch_info_t last{};
+  dexr_launch_info_t last{};  // diagnostics only; guarded by info_mu (concurrent solves on one handle are allowed)
+  std::mutex info_mu;
   // staging for dexr_solve_frames_host
   std::mutex mu;
   cudaStream_t streams[2] = {nullptr, nullptr};
@@ -555,7 +556,10 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   const int grid = std::min(a.ntiles, slots);
   kern<<<grid, (NCW + 1) * 32, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
-  r->last = dexr_launch_info_t{grid, (NCW + 1) * 32, smem, T, G, NCW, r->last.kernels_launched + 1};
+  {
+    std::lock_guard<std::mutex> lk(r->info_mu);
+    r->last = dexr_launch_info_t{grid, (NCW + 1) * 32, smem, T, G, NCW, r->last.kernels_launched + 1};
+  }
   return 0;
 }
 
@@ -608,7 +612,10 @@ static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_
   int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * (S >= (long long)r->num_sms * groups * 2 ? 2 : 1));
   kern<<<grid, kSeqNW * 32, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
-  r->last = dexr_launch_info_t{grid, kSeqNW * 32, smem, 0, G, kSeqNW, r->last.kernels_launched + 1};
+  {
+    std::lock_guard<std::mutex> lk(r->info_mu);
+    r->last = dexr_launch_info_t{grid, kSeqNW * 32, smem, 0, G, kSeqNW, r->last.kernels_launched + 1};
+  }
   return 0;
 }
 
@@ -653,6 +660,7 @@ int dexr_preprocess_keypoints(const float* raw, float* out, float* wrist_rot_out
 
 int dexr_get_launch_info(const dexr_robot_t* robot, dexr_launch_info_t* out) {
   if (!robot || !out) return fail(DEXR_E_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(const_cast<dexr_robot*>(robot)->info_mu);
   *out = robot->last;
   return 0;
 }
