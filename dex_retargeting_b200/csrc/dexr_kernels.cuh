@@ -531,14 +531,18 @@ struct Solver {
           // used throughout (identical inside the quadratic zone)
           const float ax_ = fabsf(rx), ay_ = fabsf(ry), az_ = fabsf(rz);
           rmax = fmaxf(rmax, fmaxf(ax_, fmaxf(ay_, az_)));
-          const float wx = 1.0f / fmaxf(ax_, beta), wy = 1.0f / fmaxf(ay_, beta), wz = 1.0f / fmaxf(az_, beta);
+          // 1/beta exactly inside the quadratic zone; beyond it the fast reciprocal (<= 2 ulp) is plenty: it only
+          // scales a unit-magnitude gradient component and the majoriser curvature
+          const float wx = ax_ < beta ? inv_beta : __fdividef(1.0f, ax_);
+          const float wy = ay_ < beta ? inv_beta : __fdividef(1.0f, ay_);
+          const float wz = az_ < beta ? inv_beta : __fdividef(1.0f, az_);
           gx = T.w * rx * wx; gy = T.w * ry * wy; gz = T.w * rz * wz;
           y0 = T.w * wx * j0; y1 = T.w * wy * j1; y2 = T.w * wz * j2;
         } else {
           const float d = sqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
           rmax = fmaxf(rmax, d);
           const bool quad = d < beta;
-          const float invd = d > 0.f ? 1.0f / d : 0.f;
+          const float invd = d > 0.f ? __frcp_rn(d) : 0.f;
           const float ux = rx * invd, uy = ry * invd, uz = rz * invd;
           const float hp = quad ? d * inv_beta : 1.0f;
           gx = T.w * hp * ux; gy = T.w * hp * uy; gz = T.w * hp * uz;
