@@ -339,10 +339,20 @@ def main():
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         mean_launch_ms = statistics.mean(launch_ms)
         achieved = BYTES_PER_FRAME * B / (mean_launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue = None, None
         tpath = ROOT / "profiles" / "roofline_traffic.json"
         if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tpath.read_text())
+            traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("warp_inst_per_launch"):
+                # what actually bounds the solver: warp-instruction issue (4 schedulers/SM, 1 inst/clk each).  Instruction
+                # count from the committed ncu capture of this workload, rate from the live launch time and max SM clock.
+                sm_mhz = (clk.summary() or {}).get("sm_max_mhz") or 1965
+                peak_issue = 4 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6
+                ach_issue = tj["warp_inst_per_launch"] / (mean_launch_ms * 1e-3)
+                issue = {"achieved": ach_issue, "peak": peak_issue, "unit": "warp-inst/s", "frac": ach_issue / peak_issue,
+                         "warp_inst_per_frame": tj["warp_inst_per_launch"] / B,
+                         "source": "profiles/roofline_traffic.json (ncu smsp__inst_executed.sum) / live launch time"}
         value = B * world * args.steps / (total_ms * 1e-3)
         line = {
             "metric": "hand_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -351,7 +361,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_frame": BYTES_PER_FRAME,
                          "launch_ms_mean": mean_launch_ms, "launch_ms_min": min(launch_ms), "launch_ms_max": max(launch_ms),
-                         "note": "latency/FP32-issue bound solver: see DESIGN.md for the instruction-level roofline"},
+                         "note": "latency/FP32-issue bound solver: see `issue` and DESIGN.md for the instruction-level roofline",
+                         "issue": issue},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * (252 + 64),
                     "d2h_bytes_per_step": B * 64, "ms_per_step": e2e_ms, "steps": e2e_steps, "checksum": checksum,
                     "api": "Optimizer.retarget_batch_host -> dexr_solve_frames_host, pinned host buffers in and out; zero-copy: the "

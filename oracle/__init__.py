@@ -14,14 +14,19 @@ What it restates (reference file:line, relative to /root/reference):
   * oracle/solvers.py    optimizer.py:77-102 (nlopt LD_SLSQP driver; scipy's SLSQP -- the same Kraft
                          code -- is the stand-in), seq_retarget.py:112-134, optimizer_utils.py:1-17
 
-PARITY UNPINNED.  The arithmetic of the reference path lives in third-party packages that are not
-vendored, not installed in the build container and not installable offline: pinocchio (pin>=3.3.1),
-nlopt (nlopt>=2.8.0) and torch CPU autograd (pyproject.toml:30-38).  The reference's own tests hold
-no golden joint vectors -- only the bar "mean task-space error < 1e-2 m over 100 seeded problems"
-(tests/test_optimizer.py:141,209,278) and two docstring examples (optimizer.py:411-412, :434-438).
-The oracle is pinned against exactly those (tests/test_oracle_*.py) and against internal
-consistency checks (analytic vs finite-difference Jacobians, closed-form vs torch-autograd
-gradients, two independent FK implementations), nothing stronger exists offline.
+PARITY UNPINNED at the third-party boundary, pinned above it.  pinocchio (pin>=3.3.1) and nlopt
+(nlopt>=2.8.0) are not vendored, not installed in the build container and not installable offline
+(pyproject.toml:30-38), and the reference's own tests hold no golden joint vectors -- only the bar
+"mean task-space error < 1e-2 m over 100 seeded problems" (tests/test_optimizer.py:141,209,278) and
+two docstring examples (optimizer.py:411-412, :434-438).  So:
+  * everything ABOVE those two packages is pinned by executing the reference's own optimizer.py /
+    kinematics_adaptor.py / seq_retarget.py / optimizer_utils.py on seeded inputs with the two packages
+    shimmed (tests/tools/gen_reference_vectors.py -> tests/golden/reference_vectors.npz): objective
+    values, gradients, DexPilot flags, retarget() results and SeqRetargeting streams, reproduced by
+    this oracle in tests/test_reference_vectors.py;
+  * pinocchio's FK/Jacobian VALUES and nlopt's SLSQP ITERATES stay unpinned: the oracle's kinematics
+    are checked by internal consistency only (two independent FK implementations, analytic vs
+    finite-difference Jacobians) and scipy's SLSQP stands in for nlopt's.
 
 Two solver modes:
   mode A "reference-faithful": objective value WITHOUT the norm_delta term, gradient WITH it
