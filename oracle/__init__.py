@@ -24,6 +24,10 @@ two docstring examples (optimizer.py:411-412, :434-438).  So:
     shimmed (tests/tools/gen_reference_vectors.py -> tests/golden/reference_vectors.npz): objective
     values, gradients, DexPilot flags, retarget() results and SeqRetargeting streams, reproduced by
     this oracle in tests/test_reference_vectors.py;
+  * the robot model INPUT (joint tree, origins, axes, limits, mimic lists, dummy free joints) is pinned
+    by executing the reference's own yourdfpy.py parser on every hand URDF
+    (tests/tools/gen_reference_urdf_vectors.py -> tests/golden/reference_urdf_vectors.npz,
+    tests/test_reference_urdf_vectors.py);
   * pinocchio's FK/Jacobian VALUES and nlopt's SLSQP ITERATES stay unpinned: the oracle's kinematics
     are checked by internal consistency only (two independent FK implementations, analytic vs
     finite-difference Jacobians) and scipy's SLSQP stands in for nlopt's.
