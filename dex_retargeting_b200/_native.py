@@ -27,7 +27,7 @@ class DexrTable(C.Structure):
     _fields_ = [
         ("magic", _u), ("nbytes", _u), ("dof", _i), ("n_var", _i), ("n_fixed", _i), ("n_links", _i),
         ("n_res", _i), ("loss", _i), ("n_rounds", _i), ("has_mimic", _i), ("num_fingers", _i),
-        ("len_proj", _i), ("len_s1", _i), ("block_width", _i), ("reserved", _i * 2),
+        ("len_proj", _i), ("len_s1", _i), ("block_width", _i), ("arrow", _i), ("reserved", _i),
         ("R0", (_f * 9) * MAX_LANES), ("RA", (_f * 9) * MAX_LANES), ("RB", (_f * 9) * MAX_LANES),
         ("p0", (_f * 3) * MAX_LANES), ("d0", (_f * 3) * MAX_LANES), ("axis", (_f * 3) * MAX_LANES),
         ("jtype", _i * MAX_LANES), ("var_index", _i * MAX_LANES), ("fixed_index", _i * MAX_LANES),

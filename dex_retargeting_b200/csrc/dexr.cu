@@ -399,6 +399,38 @@ static int validate_table(const dexr_table_t* t) {
       }
     }
   }
+  if (t->arrow != 0) {
+    const int tr = t->arrow - 1;
+    if (tr < 0 || tr > 8 || t->block_width != 0 || t->has_mimic || t->n_var != t->dof || t->dof <= 16 || tr >= t->dof)
+      return fail(DEXR_E_INVALID, "robot table: arrow %d inconsistent (dof %d, mimic %d, block_width %d)", t->arrow, t->dof,
+                  t->has_mimic, t->block_width);
+    const uint32_t tmask = (1u << tr) - 1u;
+    uint32_t finger_of[DEXR_MAX_LANES] = {0};  // lane -> mask of its finger's lanes
+    int fingers = 0;
+    for (int c = 0; c < tr; ++c)
+      if (t->anc_mask[c] & ~tmask) return fail(DEXR_E_INVALID, "robot table: arrow trunk joint %d has an ancestor outside the trunk", c);
+    for (int c = tr; c < t->dof; ++c) {
+      const uint32_t chain = t->anc_mask[c] & ~tmask;  // includes c itself
+      const int fb = __builtin_ctz(chain);
+      if (fb == c) {
+        const uint32_t span = t->desc_mask[c] | (1u << c);
+        const int fw = 32 - __builtin_clz(span) - c;
+        if (fw > 8 || ++fingers > 6 || span != ((fw == 32 ? 0u : (1u << fw)) - 1u) << c)
+          return fail(DEXR_E_INVALID, "robot table: arrow finger at joint %d is not a contiguous run of <= 8 lanes (or > 6 fingers)", c);
+        for (int i = c; i < c + fw; ++i) finger_of[i] = span;
+      } else if (!((t->desc_mask[fb] >> c) & 1u)) {
+        return fail(DEXR_E_INVALID, "robot table: arrow joint %d is not below its finger's first joint %d", c, fb);
+      }
+    }
+    for (int c = tr; c < t->dof; ++c)
+      if (!finger_of[c] || (t->anc_mask[c] & ~tmask & ~finger_of[c]))
+        return fail(DEXR_E_INVALID, "robot table: arrow joint %d has ancestors in another finger", c);
+    for (int k = 0; k < t->n_res; ++k) {
+      uint32_t m = (t->link_anc_mask[t->res_task[k]] | (t->res_origin[k] >= 0 ? t->link_anc_mask[t->res_origin[k]] : 0u)) & ~tmask;
+      if (m && (m & ~finger_of[__builtin_ctz(m)]))
+        return fail(DEXR_E_INVALID, "robot table: arrow but residual %d couples two fingers", k);
+    }
+  }
   for (int c = 0; c < t->dof; ++c) {
     int n = 0;
     for (int k = 0; k < t->n_links; ++k) n += (t->link_parent[k] == c);
@@ -520,6 +552,7 @@ static Dims make_dims(const dexr_table_t& t) {
   d.n_rounds = t.n_rounds; d.has_mimic = t.has_mimic; d.num_fingers = t.num_fingers; d.len_proj = t.len_proj;
   d.len_s1 = t.len_s1;
   d.block_width = t.block_width;
+  d.trunk = t.arrow > 0 ? t.arrow - 1 : 0;
   return d;
 }
 
@@ -583,6 +616,12 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
     return launch_frames<16, 0, 15>(r, params, io, num_frames, stream);
   }
   // one frame per warp: 16 warps x 128 registers (small spills) or 12 warps x 168 registers
+  // trunk + decoupled fingers (Shadow hand, any hand on a free-flying base): arrow factorisation
+  static const bool no_arrow = [] {  // until verified on a B200: opt-in with DEXR_ARROW=1
+    const char* e = getenv("DEXR_ARROW");
+    return !(e && atoi(e) != 0);
+  }();
+  if (t.arrow > 0 && !no_arrow) return launch_frames<32, -1, 15>(r, params, io, num_frames, stream);
   static const bool wide = [] { const char* e = getenv("DEXR_G32_WARPS"); return !(e && atoi(e) == 12); }();
   return wide ? launch_frames<32, 0, 15>(r, params, io, num_frames, stream)
               : launch_frames<32, 0, 11>(r, params, io, num_frames, stream);
@@ -637,6 +676,11 @@ extern "C" int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params
     if (t.block_width == 4) return launch_sequences<16, 4>(r, params, io, num_streams, (int)num_steps, stream);
     return launch_sequences<16, 0>(r, params, io, num_streams, (int)num_steps, stream);
   }
+  static const bool no_arrow = [] {  // until verified on a B200: opt-in with DEXR_ARROW=1
+    const char* e = getenv("DEXR_ARROW");
+    return !(e && atoi(e) != 0);
+  }();
+  if (t.arrow > 0 && !no_arrow) return launch_sequences<32, -1>(r, params, io, num_streams, (int)num_steps, stream);
   return launch_sequences<32, 0>(r, params, io, num_streams, (int)num_steps, stream);
 }
 

@@ -128,6 +128,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 struct Dims {
   int dof, n_var, n_fixed, n_links, n_res, loss, n_rounds, has_mimic, num_fingers, len_proj, len_s1;
   int block_width;  // 0 = dense Hessian; 4 / 8 = the Hessian is block diagonal over aligned lane windows of this width
+  int trunk;        // arrow mode only: number of trunk lanes (lanes 0..trunk-1), see Solver
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -224,8 +225,17 @@ struct FrameInputs {
 template <int G, int BW = 0>
 struct Solver {
   static constexpr int NP = G;
-  static_assert(BW == 0 || (BW % 4 == 0 && BW < G), "block width must be a multiple of 4 below the group width");
-  static constexpr int HN = (BW == 0) ? G : BW;  // Hessian row segment held per lane
+  // BW == 0: dense.  BW > 0: block diagonal over aligned windows of BW lanes.  BW < 0: ARROW -- a trunk (lanes
+  // 0..t-1, t <= 8: free-flying base and / or wrist) shared by decoupled fingers (contiguous lane runs of <= 8 joints):
+  // H = [F B; B^T W] with F block diagonal.  A finger lane keeps its own finger's row segment (registers 0..7, column
+  // fb + j) and its coupling to the trunk (registers 8..15, column j - 8); a trunk lane keeps its row of W in
+  // registers 8..15.  Fingers are eliminated side by side (<= 8 pivot steps for all of them), the trunk sees their
+  // Schur complement, then the t x t trunk system is factorised: ~13 pivot steps instead of 30 for the Shadow hand
+  // on a free-flying base, and half the registers.
+  static_assert(BW <= 0 || (BW % 4 == 0 && BW < G), "block width must be a multiple of 4 below the group width");
+  static_assert(BW >= 0 || G == 32, "arrow mode is a 32-lane layout");
+  static constexpr bool AR = BW < 0;
+  static constexpr int HN = (BW == 0) ? G : (AR ? 16 : BW);  // Hessian row segment held per lane
   using SC = Scratch<G>;
 
   // ---- lane constants kept in registers (the 3x4 joint placement lives in shared memory) ----
@@ -475,6 +485,22 @@ struct Solver {
     int rechecks = 0;
     unsigned last_fmask = 0u;
 
+    // ---- arrow mode: this lane's finger window (see the Solver comment); loop invariant ----
+    int ar_t = 0, ar_fb = 0, ar_fw = 0, ar_maxw = 0, ar_fo = 0;
+    bool ar_trunk = false;
+    if constexpr (AR) {
+      ar_t = dm.trunk;
+      ar_trunk = l < ar_t;
+      const uint32_t tmask = (1u << ar_t) - 1u;
+      const bool fin = !ar_trunk && l < dof;
+      ar_fb = fin ? __ffs((anc | (1u << l)) & ~tmask) - 1 : 0;  // the finger's first joint: lowest non-trunk ancestor
+      const unsigned bases = gballot<G>(fin && ar_fb == l, lane);
+      ar_fo = fin ? 8 * (1 + __popc(bases & ((1u << ar_fb) - 1u))) : 0;  // this finger's slot in the small row buffers
+      const uint32_t dmask = (uint32_t)gshfl_i<G>((int)desc, ar_fb) | (1u << ar_fb);
+      ar_fw = fin ? (32 - __clz(dmask)) - ar_fb : 0;
+      ar_maxw = (int)gmax<G>((float)ar_fw);
+    }
+
     while (gany<32>(!done, lane)) {
       // ======================= gradient + exact Hessian at x ===========================
       float H[HN];
@@ -557,8 +583,32 @@ struct Solver {
         jbuf(b, 0)[l] = j0; jbuf(b, 1)[l] = j1; jbuf(b, 2)[l] = j2;
         __syncwarp();
         const uint32_t cols = mt | mo;
+        if constexpr (AR) {
+          // trunk columns (aligned float4 chunks at lanes 0.. and 4..) into registers 8..15
 #pragma unroll
-        for (int blk = 0; blk < HN / 4; ++blk) {
+          for (int blk = 0; blk < 2; ++blk) {
+            if (4 * blk < ar_t) {
+              const float4 c0 = *reinterpret_cast<const float4*>(jbuf(b, 0) + 4 * blk);
+              const float4 c1 = *reinterpret_cast<const float4*>(jbuf(b, 1) + 4 * blk);
+              const float4 c2 = *reinterpret_cast<const float4*>(jbuf(b, 2) + 4 * blk);
+              H[8 + 4 * blk + 0] = fmaf(c0.x, y0, fmaf(c1.x, y1, fmaf(c2.x, y2, H[8 + 4 * blk + 0])));
+              H[8 + 4 * blk + 1] = fmaf(c0.y, y0, fmaf(c1.y, y1, fmaf(c2.y, y2, H[8 + 4 * blk + 1])));
+              H[8 + 4 * blk + 2] = fmaf(c0.z, y0, fmaf(c1.z, y1, fmaf(c2.z, y2, H[8 + 4 * blk + 2])));
+              H[8 + 4 * blk + 3] = fmaf(c0.w, y0, fmaf(c1.w, y1, fmaf(c2.w, y2, H[8 + 4 * blk + 3])));
+            }
+          }
+          // own finger's columns fb .. fb + fw - 1 (unaligned: scalar loads, one address per finger) into registers 0..7
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < ar_maxw) {
+              const int cj = ar_fb + j < NP ? ar_fb + j : NP - 1;
+              const float v = fmaf(jbuf(b, 0)[cj], y0, fmaf(jbuf(b, 1)[cj], y1, jbuf(b, 2)[cj] * y2));
+              H[j] += j < ar_fw ? v : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int blk = 0; blk < (AR ? 0 : HN / 4); ++blk) {
           if (4 * blk < bw && (!dense || ((cols >> (4 * blk)) & 0xFu))) {
             const int c4 = cb + 4 * blk;  // first of the four columns this chunk accumulates
             const float4 c0 = *reinterpret_cast<const float4*>(jbuf(b, 0) + c4);
@@ -571,6 +621,10 @@ struct Solver {
           }
         }
       }
+      if constexpr (AR) {  // the aligned trunk chunks also swept columns ar_t..7 (finger lanes): not trunk couplings
+#pragma unroll
+        for (int c = 0; c < 8; ++c) H[8 + c] = c < ar_t ? H[8 + c] : 0.f;
+      }
       // ---- FK curvature: S[i][c] = a_i . t_c (i ancestor-or-self of c), symmetric otherwise ----
       {
         const float ar0 = rev ? a[0] : 0.f, ar1 = rev ? a[1] : 0.f, ar2 = rev ? a[2] : 0.f;
@@ -580,15 +634,17 @@ struct Solver {
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < HN; ++j) {
-          if (j < bw) {
-            const int i = cb + j;  // the joint this register column stands for
+          if (AR ? (j < 8 ? j < ar_maxw : j - 8 < ar_t) : j < bw) {
+            // the joint this register column stands for (arrow mode: clamped; columns a lane does not own add 0 below)
+            const int i = AR ? (j < 8 ? (ar_fb + j < NP ? ar_fb + j : NP - 1) : j - 8) : cb + j;
             const float4 ai = at()[2 * i];
             const float4 ti_ = at()[2 * i + 1];
             const bool up = (anc >> i) & 1u;
             const bool dn = (desc >> i) & 1u;
             const float vu = fmaf(ai.x, t0, fmaf(ai.y, t1, ai.z * t2));
             const float vd = fmaf(ar0, ti_.x, fmaf(ar1, ti_.y, ar2 * ti_.z));
-            H[j] += curv_on ? (up ? vu : (dn ? vd : 0.f)) : 0.f;
+            const bool mine = !AR || (j < 8 ? j < ar_fw : true);
+            H[j] += (curv_on && mine) ? (up ? vu : (dn ? vd : 0.f)) : 0.f;
           }
         }
       }
@@ -651,9 +707,11 @@ struct Solver {
       if (gany<32>(l < dof && !free_, lane)) {
 #pragma unroll
         for (int j = 0; j < HN; ++j) {
-          const bool keep = free_ && ((fmask >> (cb + j)) & 1u);
+          // the column register j stands for (arrow mode: -1 where this lane owns none)
+          const int cj = AR ? (j < 8 ? (j < ar_fw ? ar_fb + j : -1) : (j - 8 < ar_t ? j - 8 : -1)) : cb + j;
+          const bool keep = free_ && cj >= 0 && ((fmask >> (cj & 31)) & 1u);
           float v = keep ? H[j] : 0.f;
-          if (cb + j == l && !free_) v = 1.0f;
+          if (cj == l && !free_ && (!AR || ar_trunk == (j >= 8))) v = 1.0f;
           H[j] = v;
         }
       }
@@ -664,7 +722,8 @@ struct Solver {
       // own diagonal entry (register index = lane id is not addressable: read it back from the column store);
       // the regulariser 2*norm_delta enters on the diagonal at pivot time together with the damping
       const float reg2 = free_ ? 2.0f * nd : 0.f;
-      const float hd = free_ ? hbuf[(l - cb) * NP + l] + reg2 : 1.0f;
+      const int dj = AR ? (ar_trunk ? 8 + l : l - ar_fb) : l - cb;  // register holding this lane's diagonal entry
+      const float hd = free_ ? hbuf[dj * NP + l] + reg2 : 1.0f;
       const float D = fabsf(hd) + 1e-6f;
       // ======================= damped Newton trials ====================================
       bool accepted = done;
@@ -686,7 +745,151 @@ struct Solver {
         // left (fused into the update FMA), so the pivot column is always register H[0] and the loop body is
         // the same code for every k -- 16-32x less code than the unrolled form (instruction-cache bound
         // otherwise), same FMA count thanks to the chunk guard.
-        for (int k = 0; k < bw; ++k) {
+        if constexpr (AR) {
+          // ================= arrow factorisation: fingers side by side, Schur complement, trunk =================
+          // Scratch (all inside regions that are idle here): rowb = two alternating sets of per-finger row segments
+          // (8 floats per finger slot, slot 0 = trunk), tbuf = per-finger broadcast of the pivot's scaled trunk
+          // coupling, M = [lane][12] finger lanes' L_TF column + forward-substituted rhs (upper half of the backup
+          // area, which arrow mode does not use).
+          float* rowb = Lr;            // [2][64]
+          float* tbuf = Lr + 128;      // [64]
+          float* M = hb() + 16 * NP;   // [NP][12]
+          const bool fin = !ar_trunk && l < dof;
+          // ---- finger phase: step s eliminates joint fb + s of every finger at once ----
+          for (int s_ = 0; s_ < ar_maxw; ++s_) {
+            const int pk = ar_fb + s_;
+            const bool act = fin && s_ < ar_fw;
+            float hk = H[0];
+            if (act && pk == l) hk += fmaf(lam, D, reg2);
+            const float dkk = gshfl<G>(hk, act ? pk : l);
+            bad = bad || (act && !(dkk > 1e-20f));
+            const float inv = act ? rsqrtf(fmaxf(dkk, 1e-20f)) : 1.0f;
+            const float lik = hk * inv;                            // L[l][pk] for l >= pk
+            const float yk = gshfl<G>(y, act ? pk : l) * inv;      // forward substitution fused
+            const bool piv = act && l == pk, below = act && l > pk;
+            if (piv) {
+              myinv = inv; y = yk;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) H[8 + c] *= inv;          // L_TF[c][pk], final
+              *reinterpret_cast<float4*>(tbuf + ar_fo) = make_float4(H[8], H[9], H[10], H[11]);
+              *reinterpret_cast<float4*>(tbuf + ar_fo + 4) = make_float4(H[12], H[13], H[14], H[15]);
+            }
+            if (below) y = fmaf(-lik, yk, y);
+            float* row = rowb + (s_ & 1) * 64 + ar_fo;
+            if (below) row[l - pk - 1] = lik;                       // entry j of the segment = L[pk+1+j][pk]
+            Lc[s_ * (NP + 1) + l] = (act && l >= pk) ? lik : 0.f;   // transposed copy for the back substitution
+            __syncwarp();
+            if (gany<32>(below, lane)) {
+              const int live = ar_fw - s_ - 1;                      // columns right of the pivot inside the finger
+              const float4 r0 = *reinterpret_cast<const float4*>(row);
+              const float4 r1 = *reinterpret_cast<const float4*>(row + 4);
+              const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 v0 = below ? *reinterpret_cast<const float4*>(tbuf + ar_fo) : z4;      // (slot 0 is never
+              const float4 v1 = below ? *reinterpret_cast<const float4*>(tbuf + ar_fo + 4) : z4;  //  written: select)
+              const float ml = below ? -lik : 0.f;
+              // rotate the finger window one column to the left (stale segment entries beyond `live` masked out)
+              H[0] = fmaf(ml, 0 < live ? r0.x : 0.f, H[1]);
+              H[1] = fmaf(ml, 1 < live ? r0.y : 0.f, H[2]);
+              H[2] = fmaf(ml, 2 < live ? r0.z : 0.f, H[3]);
+              H[3] = fmaf(ml, 3 < live ? r0.w : 0.f, H[4]);
+              H[4] = fmaf(ml, 4 < live ? r1.x : 0.f, H[5]);
+              H[5] = fmaf(ml, 5 < live ? r1.y : 0.f, H[6]);
+              H[6] = fmaf(ml, 6 < live ? r1.z : 0.f, H[7]);
+              H[7] = 0.f;
+              // trunk coupling of the rows below the pivot (finished rows keep their final L_TF: ml = 0)
+              H[8] = fmaf(ml, v0.x, H[8]);   H[9] = fmaf(ml, v0.y, H[9]);
+              H[10] = fmaf(ml, v0.z, H[10]); H[11] = fmaf(ml, v0.w, H[11]);
+              H[12] = fmaf(ml, v1.x, H[12]); H[13] = fmaf(ml, v1.y, H[13]);
+              H[14] = fmaf(ml, v1.z, H[14]); H[15] = fmaf(ml, v1.w, H[15]);
+            }
+            __syncwarp();
+          }
+          // ---- Schur complement: W -= L_TF L_TF^T, rhs_T -= L_TF y_F; every lane takes a quarter of the finger rows
+          M[l * 12 + 8] = fin ? y : 0.f;
+          *reinterpret_cast<float4*>(M + l * 12) = fin ? make_float4(H[8], H[9], H[10], H[11]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(M + l * 12 + 4) = fin ? make_float4(H[12], H[13], H[14], H[15]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
+          {
+            const int c = l & 7, qd = l >> 3;
+            float acc[9];
+#pragma unroll
+            for (int d = 0; d < 9; ++d) acc[d] = 0.f;
+            for (int i = ar_t + qd; i < dof; i += 4) {
+              const float mc = M[i * 12 + c];
+              const float4 m0 = *reinterpret_cast<const float4*>(M + i * 12);
+              const float4 m1 = *reinterpret_cast<const float4*>(M + i * 12 + 4);
+              acc[0] = fmaf(mc, m0.x, acc[0]); acc[1] = fmaf(mc, m0.y, acc[1]);
+              acc[2] = fmaf(mc, m0.z, acc[2]); acc[3] = fmaf(mc, m0.w, acc[3]);
+              acc[4] = fmaf(mc, m1.x, acc[4]); acc[5] = fmaf(mc, m1.y, acc[5]);
+              acc[6] = fmaf(mc, m1.z, acc[6]); acc[7] = fmaf(mc, m1.w, acc[7]);
+              acc[8] = fmaf(mc, M[i * 12 + 8], acc[8]);
+            }
+#pragma unroll
+            for (int d = 0; d < 9; ++d) {
+              acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 8);
+              acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 16);
+            }
+            if (ar_trunk) {  // lane l < t <= 8: c == l
+#pragma unroll
+              for (int d = 0; d < 8; ++d) H[8 + d] -= acc[d];
+              y -= acc[8];
+            }
+          }
+          // ---- trunk phase: dense rotating Cholesky of the t x t Schur complement on the trunk lanes ----
+          for (int k = 0; k < ar_t; ++k) {
+            float hk = H[8];
+            if (k == l) hk += fmaf(lam, D, reg2);
+            const float dkk = gshfl<G>(hk, k);
+            bad = bad || !(dkk > 1e-20f);
+            const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
+            const float lik = hk * inv;
+            const float yk = gshfl<G>(y, k) * inv;
+            const bool below = ar_trunk && l > k;
+            if (l == k) { myinv = inv; y = yk; }
+            if (below) y = fmaf(-lik, yk, y);
+            float* row = rowb + (k & 1) * 64;
+            if (below) row[l - k - 1] = lik;
+            Lc[(8 + k) * (NP + 1) + l] = lik;
+            __syncwarp();
+            const int live = ar_t - k - 1;
+            const float4 r0 = *reinterpret_cast<const float4*>(row);
+            const float4 r1 = *reinterpret_cast<const float4*>(row + 4);
+            const float ml = below ? -lik : 0.f;
+            H[8] = fmaf(ml, 0 < live ? r0.x : 0.f, H[9]);
+            H[9] = fmaf(ml, 1 < live ? r0.y : 0.f, H[10]);
+            H[10] = fmaf(ml, 2 < live ? r0.z : 0.f, H[11]);
+            H[11] = fmaf(ml, 3 < live ? r0.w : 0.f, H[12]);
+            H[12] = fmaf(ml, 4 < live ? r1.x : 0.f, H[13]);
+            H[13] = fmaf(ml, 5 < live ? r1.y : 0.f, H[14]);
+            H[14] = fmaf(ml, 6 < live ? r1.z : 0.f, H[15]);
+            H[15] = 0.f;
+            __syncwarp();
+          }
+          // ---- back substitution: trunk, then the fingers with the trunk solution folded into their rhs ----
+          for (int k = ar_t - 1; k >= 0; --k) {
+            const float xk = gshfl<G>(y * myinv, k);
+            if (l == k) y = xk;
+            if (ar_trunk && l < k) y = fmaf(-Lc[(8 + l) * (NP + 1) + k], xk, y);
+          }
+          {
+            const float4 m0 = *reinterpret_cast<const float4*>(M + l * 12);
+            const float4 m1 = *reinterpret_cast<const float4*>(M + l * 12 + 4);
+            float corr = 0.f;
+            corr = fmaf(m0.x, gshfl<G>(y, 0), corr); corr = fmaf(m0.y, gshfl<G>(y, 1), corr);
+            corr = fmaf(m0.z, gshfl<G>(y, 2), corr); corr = fmaf(m0.w, gshfl<G>(y, 3), corr);
+            corr = fmaf(m1.x, gshfl<G>(y, 4), corr); corr = fmaf(m1.y, gshfl<G>(y, 5), corr);
+            corr = fmaf(m1.z, gshfl<G>(y, 6), corr); corr = fmaf(m1.w, gshfl<G>(y, 7), corr);
+            if (fin) y -= corr;  // entries beyond t are zero in M (H[8 + c] stays 0 for c >= t)
+          }
+          for (int s_ = ar_maxw - 1; s_ >= 0; --s_) {
+            const int pk = ar_fb + s_;
+            const bool act = fin && s_ < ar_fw;
+            const float xk = gshfl<G>(y * myinv, act ? pk : l);
+            if (act && l == pk) y = xk;
+            if (act && l < pk) y = fmaf(-Lc[(l - ar_fb) * (NP + 1) + pk], xk, y);
+          }
+        }
+        for (int k = 0; k < (AR ? 0 : bw); ++k) {
           const int pk = cb + k;  // pivot lane (of this lane's block)
           float hk = H[0];
           if (pk == l) hk += fmaf(lam, D, reg2);
@@ -714,7 +917,7 @@ struct Solver {
           }
         }
         // back substitution: L^T delta = y (column oriented, transposed copy read conflict free)
-        for (int k = bw - 1; k >= 0; --k) {
+        for (int k = (AR ? 0 : bw) - 1; k >= 0; --k) {
           const int pk = cb + k;
           const float xk = gshfl<G>(y * myinv, pk);
           if (l == pk) y = xk;

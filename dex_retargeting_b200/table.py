@@ -204,6 +204,7 @@ def compile_table(
         else:
             t.res_task[k], t.res_origin[k], t.res_human_task[k], t.res_human_origin[k] = 0, -1, 0, -1
     t.block_width = _block_width(t, dof, n_var, has_mimic)
+    t.arrow = 0 if t.block_width else _arrow(t, dof, n_var, has_mimic)
     t.num_fingers, t.len_proj, t.len_s1 = objective.num_fingers, objective.len_proj, objective.len_s1
     for k in range(N.MAX_RES):
         t.s2_origin[k] = objective.s2_origin[k] if k < len(objective.s2_origin) else 0
@@ -246,6 +247,53 @@ def _block_width(t: N.DexrTable, dof: int, n_var: int, has_mimic: int) -> int:
     for bw in (4, 8):
         if dof % bw == 0 and bw < dof and all(min(v) // bw == max(v) // bw for v in comps.values()):
             return bw
+    return 0
+
+
+def _arrow(t: N.DexrTable, dof: int, n_var: int, has_mimic: int) -> int:
+    """1 + the number of trunk lanes if the Newton system has ARROW structure, else 0 (include/dexr.h: `arrow`).
+
+    Trunk = lanes 0..tr-1 (a free-flying base and / or wrist joints: pinocchio's depth-first order puts the shared
+    chain first); what remains must split into fingers -- contiguous lane runs of at most 8 joints headed by an
+    ancestor of the rest -- such that no residual block and no ancestor relation joins two fingers.  The smallest such
+    trunk (at most 8 lanes) is taken.  Only used by the 32-lane solver (dof > 16)."""
+    if has_mimic or n_var != dof or dof <= 16:
+        return 0
+    anc = [int(t.anc_mask[c]) for c in range(dof)]
+    desc = [int(t.desc_mask[c]) for c in range(dof)]
+    supports = []
+    for k in range(t.n_res):
+        m = int(t.link_anc_mask[t.res_task[k]])
+        if t.res_origin[k] >= 0:
+            m |= int(t.link_anc_mask[t.res_origin[k]])
+        supports.append(m)
+    for tr in range(0, min(8, dof - 1) + 1):
+        tmask = (1 << tr) - 1
+        if any(anc[c] & ~tmask for c in range(tr)):
+            continue
+        finger_of, fingers, ok = {}, 0, True
+        for c in range(tr, dof):
+            chain = anc[c] & ~tmask
+            fb = (chain & -chain).bit_length() - 1
+            if fb == c:
+                span = desc[c] | (1 << c)
+                fw = span.bit_length() - c
+                if fw > 8 or span != ((1 << fw) - 1) << c:
+                    ok = False
+                    break
+                fingers += 1
+                for i in range(c, c + fw):
+                    finger_of[i] = span
+            elif not (desc[fb] >> c) & 1:
+                ok = False
+                break
+        if not ok or fingers > 6 or fingers < 2:
+            continue
+        if any(c not in finger_of or (anc[c] & ~tmask & ~finger_of[c]) for c in range(tr, dof)):
+            continue
+        if any((m & ~tmask) and ((m & ~tmask) & ~finger_of[((m & ~tmask) & -(m & ~tmask)).bit_length() - 1]) for m in supports):
+            continue
+        return 1 + tr
     return 0
 
 

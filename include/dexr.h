@@ -76,7 +76,13 @@ typedef struct dexr_table {
   int32_t block_width; /* 0: dense Hessian.  4 / 8: the joints split into decoupled groups occupying aligned lane
                           windows of this width (no residual and no ancestor relation crosses a window), so the
                           Newton system is block diagonal and all blocks are factorised side by side */
-  int32_t reserved[2];
+  int32_t arrow;       /* 0: none.  1 + t: ARROW structure -- lanes 0..t-1 (t <= 8) are a trunk (free-flying base and / or
+                          wrist) shared by decoupled fingers, each a contiguous run of <= 8 lanes whose first lane is an
+                          ancestor of the others; every residual touches the trunk and at most one finger.  The Newton
+                          system is then H = [F B; B^T W] with F block diagonal and is factorised finger by finger
+                          (side by side) + a t x t Schur complement.  Requires block_width == 0, no mimic joints,
+                          n_var == dof, dof > 16 */
+  int32_t reserved;
 
   /* ---- per lane ---- */
   float R0[DEXR_MAX_LANES][9];    /* joint placement rotation in the parent joint frame          */

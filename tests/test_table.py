@@ -200,3 +200,37 @@ def test_library_rejects_inconsistent_block_width():
     assert b"couples two windows" in lib.dexr_last_error()
     t.block_width = 5
     assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
+
+
+def test_arrow_detection():
+    """A trunk (free-flying base and / or wrist) above decoupled fingers -> arrow factorisation (1 + trunk lanes)."""
+    expect = {"offline/shadow_hand_right": 9,            # 6 dummy joints + WRJ2 + WRJ1, fingers 4/5/4/4/5
+              "teleop/shadow_hand_left": 3,               # WRJ2 + WRJ1
+              "offline/allegro_hand_right": 7, "offline/leap_hand_left": 7,   # 6 dummy joints, 4 fingers x 4
+              "teleop/shadow_hand_right_dexpilot": 0,     # finger-pair vectors couple the fingers
+              "teleop/allegro_hand_right": 0,             # block diagonal already (block_width 4)
+              "offline/schunk_svh_hand_right": 0, "offline/inspire_hand_left": 0,  # mimic joints: dense path
+              "teleop/leap_hand_right_dexpilot": 0}
+    for key, arrow in expect.items():
+        t = build_product(key).optimizer.build_table()
+        assert t.arrow == arrow, key
+        assert not (t.arrow and t.block_width)
+
+
+def test_library_rejects_inconsistent_arrow():
+    import ctypes as C
+
+    lib = N.load()
+    h = C.c_void_p()
+    t = build_product("teleop/shadow_hand_right_dexpilot").optimizer.build_table()
+    t.arrow = 3  # pair vectors couple two fingers
+    assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
+    assert b"couples two fingers" in lib.dexr_last_error()
+    t = build_product("teleop/shadow_hand_right").optimizer.build_table()
+    t.arrow = 2  # WRJ1 would head a "finger" of 23 joints
+    assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
+    assert b"arrow" in lib.dexr_last_error()
+    t = build_product("offline/schunk_svh_hand_right").optimizer.build_table()
+    t.arrow = 7  # mimic joints
+    assert lib.dexr_robot_create(C.byref(t), 0, C.byref(h)) == -1
+    assert b"inconsistent" in lib.dexr_last_error()
