@@ -556,6 +556,13 @@ static Dims make_dims(const dexr_table_t& t) {
   return d;
 }
 
+// Read per call (a getenv is nanoseconds against a launch) so that tests can compare the arrow and the dense
+// factorisation inside one process.  Until verified on a B200: opt-in with DEXR_ARROW=1.
+static bool arrow_enabled() {
+  const char* e = getenv("DEXR_ARROW");
+  return e && atoi(e) != 0;
+}
+
 template <int G, int BW, int NCW>
 static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
   const dexr_table_t& t = r->host;
@@ -617,10 +624,7 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   }
   // one frame per warp: 16 warps x 128 registers (small spills) or 12 warps x 168 registers
   // trunk + decoupled fingers (Shadow hand, any hand on a free-flying base): arrow factorisation
-  static const bool no_arrow = [] {  // until verified on a B200: opt-in with DEXR_ARROW=1
-    const char* e = getenv("DEXR_ARROW");
-    return !(e && atoi(e) != 0);
-  }();
+  const bool no_arrow = !arrow_enabled();
   if (t.arrow > 0 && !no_arrow) return launch_frames<32, -1, 15>(r, params, io, num_frames, stream);
   static const bool wide = [] { const char* e = getenv("DEXR_G32_WARPS"); return !(e && atoi(e) == 12); }();
   return wide ? launch_frames<32, 0, 15>(r, params, io, num_frames, stream)
@@ -676,10 +680,7 @@ extern "C" int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params
     if (t.block_width == 4) return launch_sequences<16, 4>(r, params, io, num_streams, (int)num_steps, stream);
     return launch_sequences<16, 0>(r, params, io, num_streams, (int)num_steps, stream);
   }
-  static const bool no_arrow = [] {  // until verified on a B200: opt-in with DEXR_ARROW=1
-    const char* e = getenv("DEXR_ARROW");
-    return !(e && atoi(e) != 0);
-  }();
+  const bool no_arrow = !arrow_enabled();
   if (t.arrow > 0 && !no_arrow) return launch_sequences<32, -1>(r, params, io, num_streams, (int)num_steps, stream);
   return launch_sequences<32, 0>(r, params, io, num_streams, (int)num_steps, stream);
 }

@@ -1,0 +1,95 @@
+"""Arrow factorisation (trunk + decoupled fingers, include/dexr.h `arrow`) against the dense factorisation of the same
+Newton systems and against the oracle: same minimiser, |dq|_inf < 1e-4 rad, for every robot family that takes the path
+(Shadow on a free-flying base: trunk 8; Shadow teleop: trunk 2; Allegro / LEAP on a free-flying base: trunk 6), frames and
+sequences, warm and cold starts, and with joints parked on their limits (frozen rows / columns in both blocks)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import build_oracle, build_product, keypoint_trajectory, synth_problems
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import gpu_solve, oracle_b  # noqa: E402
+
+TOL = 1e-4
+ARROW_KEYS = ["offline/shadow_hand_right", "teleop/shadow_hand_left", "offline/allegro_hand_right", "offline/leap_hand_left"]
+
+
+class arrow_mode:
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = os.environ.get("DEXR_ARROW")
+        os.environ["DEXR_ARROW"] = "1" if self.on else "0"
+
+    def __exit__(self, *a):
+        if self.prev is None:
+            os.environ.pop("DEXR_ARROW", None)
+        else:
+            os.environ["DEXR_ARROW"] = self.prev
+
+
+def _problems(key, n, seed, init_noise, target_noise):
+    ov = {"scaling_factor": 1.0} if "offline" not in key else {}
+    seq, o = build_product(key, ov), build_oracle(key, ov)
+    assert seq.optimizer.build_table().arrow > 0
+    refs, fixed, x0, _ = synth_problems(o, n, np.random.RandomState(seed), init_noise=init_noise, target_noise=target_noise)
+    return seq.optimizer, o, refs, fixed, x0
+
+
+@pytest.mark.parametrize("key", ARROW_KEYS)
+def test_arrow_matches_dense_and_oracle_warm(key):
+    opt, o, refs, fixed, x0 = _problems(key, 48, 5, 0.05, 0.01)
+    with arrow_mode(True):
+        a = gpu_solve(opt, refs, fixed, x0)
+        info = opt.engine().launch_info()
+    with arrow_mode(False):
+        d = gpu_solve(opt, refs, fixed, x0)
+    assert int((a["status"] >> 24).max()) == 0 and int((d["status"] >> 24).max()) == 0
+    # same Newton systems, different elimination order: the iterates agree to rounding, the minimiser to far below TOL
+    assert np.abs(a["q"] - d["q"]).max() < 2e-5
+    np.testing.assert_allclose(a["cost"], d["cost"], rtol=1e-5, atol=1e-9)
+    assert abs(float((a["status"] & 0xffff).mean()) - float((d["status"] & 0xffff).mean())) < 0.5
+    XB, _ = oracle_b(o, refs, fixed, x0)
+    dq = np.abs(a["q"] - XB).max(1)
+    assert (dq < TOL).mean() >= 0.95 and np.median(dq) < 1e-5, (np.median(dq), dq.max())
+    assert info["lanes_per_frame"] == 32
+
+
+@pytest.mark.parametrize("key", ARROW_KEYS[:2])
+def test_arrow_cold_start_and_active_bounds(key):
+    """0.5 rad cold starts drive joints onto their limits: rows / columns frozen in the finger blocks, the coupling block and
+    the trunk block."""
+    opt, o, refs, fixed, x0 = _problems(key, 64, 9, 0.5, 0.0)
+    lim = o.joint_limits
+    x0 = x0.copy()
+    x0[::3, -3:] = lim[-3:, 1]   # start some thumb joints on the upper limit
+    x0[1::3, 0] = lim[0, 0]      # and the first trunk joint on the lower one
+    with arrow_mode(True):
+        a = gpu_solve(opt, refs, fixed, x0.astype(np.float32))
+    with arrow_mode(False):
+        d = gpu_solve(opt, refs, fixed, x0.astype(np.float32))
+    assert int((a["status"] >> 25).max()) == 0
+    same = np.abs(a["q"] - d["q"]).max(1) < TOL
+    assert same.mean() >= 0.9, same.mean()           # cold starts amplify rounding differences into basin changes now and then
+    np.testing.assert_allclose(a["cost"][same], d["cost"][same], rtol=1e-4, atol=1e-8)
+    assert abs(np.median(a["cost"]) - np.median(d["cost"])) <= 1e-6 + 0.05 * np.median(d["cost"])
+
+
+def test_arrow_sequences_match_frame_by_frame():
+    key = "teleop/shadow_hand_left"
+    dev = torch.device("cuda", 0)
+    seq = build_product(key)
+    kp = torch.from_numpy(np.ascontiguousarray(keypoint_trajectory()[None, 100:124].astype(np.float32))).to(dev)
+    with arrow_mode(True):
+        out_a, _ = seq.retarget_sequences(kp)
+    seq2 = build_product(key)
+    with arrow_mode(False):
+        out_d, _ = seq2.retarget_sequences(kp)
+    torch.cuda.synchronize()
+    assert float((out_a - out_d).abs().max()) < 5e-4  # 24 chained warm starts
+    assert float((out_a - out_d).abs().median()) < 1e-5
