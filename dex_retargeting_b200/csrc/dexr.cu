@@ -556,11 +556,11 @@ static Dims make_dims(const dexr_table_t& t) {
   return d;
 }
 
-// Read per call (a getenv is nanoseconds against a launch) so that tests can compare the arrow and the dense
-// factorisation inside one process.  Until verified on a B200: opt-in with DEXR_ARROW=1.
+// DEXR_ARROW=0 forces the dense factorisation for tables that qualify for the arrow one.  Read per call (a getenv is
+// nanoseconds against a launch) so that tests can compare the two inside one process.
 static bool arrow_enabled() {
   const char* e = getenv("DEXR_ARROW");
-  return e && atoi(e) != 0;
+  return !(e && atoi(e) == 0);
 }
 
 template <int G, int BW, int NCW>

