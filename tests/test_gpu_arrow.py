@@ -93,3 +93,33 @@ def test_arrow_sequences_match_frame_by_frame():
     torch.cuda.synchronize()
     assert float((out_a - out_d).abs().max()) < 5e-4  # 24 chained warm starts
     assert float((out_a - out_d).abs().median()) < 1e-5
+
+
+@pytest.mark.parametrize("trunk,widths,kind", [(0, (5, 5, 5, 5, 5), "vector"),      # no trunk at all, 5-wide fingers
+                                               (1, (8, 8, 8, 7), "position"),       # widest fingers, all 32 lanes in use
+                                               (3, (1, 2, 8, 3, 6, 6), "position"), # six ragged fingers
+                                               (8, (4, 5, 4, 4, 5), "vector")])     # widest trunk
+def test_arrow_on_synthetic_tree_hands(tmp_path, trunk, widths, kind):
+    """Shapes no shipped hand has: the arrow factorisation at the edges of what the table compiler accepts."""
+    from synthetic_robots import write_tree_hand
+    from dex_retargeting_b200.retargeting_config import RetargetingConfig
+    from oracle.objectives import OracleOptimizer
+
+    p, cfg = write_tree_hand(tmp_path, trunk, widths, kind=kind)
+    seq = RetargetingConfig.from_dict(dict(cfg)).build()
+    opt = seq.optimizer
+    assert opt.build_table().arrow == 1 + trunk
+    o = OracleOptimizer(dict(cfg), str(tmp_path))
+    assert o.robot.dof_joint_names == opt.robot.dof_joint_names
+    refs, fixed, x0, _ = synth_problems(o, 24, np.random.RandomState(4), init_noise=0.05, target_noise=0.003)
+    with arrow_mode(True):
+        a = gpu_solve(opt, refs, fixed, x0)
+    with arrow_mode(False):
+        d = gpu_solve(opt, refs, fixed, x0)
+    assert int((a["status"] >> 25).max()) == 0
+    same = np.abs(a["q"] - d["q"]).max(1) < TOL
+    assert same.mean() >= 0.9, (same.mean(), np.abs(a["q"] - d["q"]).max())
+    np.testing.assert_allclose(a["cost"][same], d["cost"][same], rtol=5e-4, atol=1e-8)
+    XB, _ = oracle_b(o, refs, fixed, x0)
+    dq = np.abs(a["q"] - XB).max(1)
+    assert (dq < TOL).mean() >= 0.85 and np.median(dq) < 2e-5, (np.median(dq), dq.max())
