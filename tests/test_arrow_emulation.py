@@ -41,74 +41,73 @@ def run(t, widths, dof):
             for d in range(t): H[l,8+d]=A[l,d]
         y[l]=-g[l]
     rowb=np.full((2,64),np.nan); tbuf=np.full(64,np.nan); Lc=np.full((16,NP+1),np.nan); M=np.zeros((NP,12))
-    for s in range(maxw):
-        pk=fb+s; act=fin&(s<fw)
-        hk=H[:,0].copy()
-        src=np.where(act,pk,np.arange(NP))
-        dkk=hk[src]
-        inv=np.where(act,1/np.sqrt(np.maximum(dkk,1e-20)),1.0)
-        lik=hk*inv
-        yk=y[src]*inv
-        piv=act&(np.arange(NP)==pk); below=act&(np.arange(NP)>pk)
-        for l in range(NP):
-            if piv[l]:
-                myinv[l]=inv[l]; y[l]=yk[l]; H[l,8:16]*=inv[l]; tbuf[fo[l]:fo[l]+8]=H[l,8:16]
-        for l in range(NP):
-            if below[l]: y[l]-=lik[l]*yk[l]; rowb[s&1,fo[l]+l-pk[l]-1]=lik[l]
-            Lc[s,l]=lik[l] if (act[l] and l>=pk[l]) else 0.0
-        if below.any():
+    lanes=np.arange(NP)
+    # ---- elimination: ONE step body for both passes (pass 0: every finger at once, pass 1: the trunk in the same window)
+    for ps in (0,1):
+        mine=fin if ps==0 else trunk
+        fbx=fb if ps==0 else np.zeros(NP,int); fox=fo if ps==0 else np.zeros(NP,int)
+        fwx=fw if ps==0 else np.where(trunk,t,0)
+        steps=maxw if ps==0 else t; lc0=8*ps
+        for s in range(steps):
+            pk=fbx+s; act=mine&(s<fwx)
+            hk=H[:,0].copy()
+            src=np.where(act,pk,lanes)
+            dkk=hk[src]
+            inv=np.where(act,1/np.sqrt(np.maximum(dkk,1e-20)),1.0)
+            lik=hk*inv
+            yk=y[src]*inv
+            piv=act&(lanes==pk); below=act&(lanes>pk)
             for l in range(NP):
-                live=fw[l]-s-1
-                r=rowb[s&1,fo[l]:fo[l]+8]
-                v=tbuf[fo[l]:fo[l]+8] if below[l] else np.zeros(8)
-                ml=-lik[l] if below[l] else 0.0
-                newH=H[l].copy()
-                for j in range(7): newH[j]=ml*(r[j] if j<live else 0.0)+H[l,j+1]
-                newH[7]=0
-                for cc in range(8): newH[8+cc]=ml*v[cc]+H[l,8+cc]
-                H[l]=newH
-    for l in range(NP):
-        M[l,8]=y[l] if fin[l] else 0
-        M[l,:8]=H[l,8:16] if fin[l] else 0
-    acc=np.zeros((NP,9))
-    for l in range(NP):
-        c_=l&7; qd=l>>3
-        for i in range(t+qd,dof,4):
-            acc[l,:8]+=M[i,c_]*M[i,:8]; acc[l,8]+=M[i,c_]*M[i,8]
-    tot=np.zeros((NP,9))
-    for l in range(NP):
-        for q in range(4): tot[l]+=acc[(l&7)+8*q]
-    for l in range(t): H[l,8:16]-=tot[l,:8]; y[l]-=tot[l,8]
-    for k in range(t):
-        hk=H[:,8].copy(); dkk=hk[k]; inv=1/np.sqrt(max(dkk,1e-20)); lik=hk*inv; yk=y[k]*inv
-        for l in range(NP):
-            below=trunk[l] and l>k
-            if l==k: myinv[l]=inv; y[l]=yk
-            if below: y[l]-=lik[l]*yk; rowb[k&1,l-k-1]=lik[l]
-            Lc[8+k,l]=lik[l]
-        live=t-k-1
-        for l in range(NP):
-            below=trunk[l] and l>k
-            ml=-lik[l] if below else 0.0
-            r=rowb[k&1,0:8]
-            newH=H[l].copy()
-            for j in range(7): newH[8+j]=ml*(r[j] if j<live else 0.0)+H[l,9+j]
-            newH[15]=0; H[l]=newH
-    for k in range(t-1,-1,-1):
-        xk=y[k]*myinv[k]
-        for l in range(NP):
-            if l==k: y[l]=xk
-            if trunk[l] and l<k: y[l]-=Lc[8+l,k]*xk
-    for l in range(NP):
-        if fin[l]: y[l]-=sum(M[l,cc]*y[cc] for cc in range(8))
-    for s in range(maxw-1,-1,-1):
-        pk=fb+s; act=fin&(s<fw)
-        src=np.where(act,pk,np.arange(NP)); xk=(y*myinv)[src]
-        ynew=y.copy()
-        for l in range(NP):
-            if act[l] and l==pk[l]: ynew[l]=xk[l]
-            if act[l] and l<pk[l]: ynew[l]=y[l]-Lc[l-fb[l],pk[l]]*xk[l]
-        y=ynew
+                if piv[l]:
+                    myinv[l]=inv[l]; y[l]=yk[l]
+                    if ps==0: H[l,8:16]*=inv[l]; tbuf[fox[l]:fox[l]+8]=H[l,8:16]
+            for l in range(NP):
+                if below[l]: y[l]-=lik[l]*yk[l]; rowb[s&1,fox[l]+l-pk[l]-1]=lik[l]
+                Lc[lc0+s,l]=lik[l] if (act[l] and l>=pk[l]) else 0.0
+            if below.any():
+                for l in range(NP):
+                    live=fwx[l]-s-1
+                    r=rowb[s&1,fox[l]:fox[l]+8]
+                    ml=-lik[l] if below[l] else 0.0
+                    newH=H[l].copy()
+                    for j in range(7): newH[j]=ml*(r[j] if j<live else 0.0)+H[l,j+1]
+                    newH[7]=0
+                    if ps==0:
+                        v=tbuf[fox[l]:fox[l]+8] if below[l] else np.zeros(8)
+                        for cc in range(8): newH[8+cc]=ml*v[cc]+H[l,8+cc]
+                    H[l]=newH
+        if ps==0:
+            # Schur complement by a 4-way split of the finger rows over all lanes, then the trunk rows move into the window
+            for l in range(NP):
+                M[l,8]=y[l] if fin[l] else 0
+                M[l,:8]=H[l,8:16] if fin[l] else 0
+            acc=np.zeros((NP,9))
+            for l in range(NP):
+                c_=l&7; qd=l>>3
+                for i in range(t+qd,dof,4):
+                    acc[l,:8]+=M[i,c_]*M[i,:8]; acc[l,8]+=M[i,c_]*M[i,8]
+            tot=np.zeros((NP,9))
+            for l in range(NP):
+                for q in range(4): tot[l]+=acc[(l&7)+8*q]
+            for l in range(t): H[l,0:8]=H[l,8:16]-tot[l,:8]; y[l]-=tot[l,8]
+    # ---- back substitution: one step body, trunk pass first, its solution folded into the fingers' right-hand sides
+    for ps in (1,0):
+        mine=fin if ps==0 else trunk
+        fbx=fb if ps==0 else np.zeros(NP,int)
+        fwx=fw if ps==0 else np.where(trunk,t,0)
+        steps=maxw if ps==0 else t; lc0=8*ps
+        if ps==0:
+            xt=y[:8].copy()
+            for l in range(NP):
+                if fin[l]: y[l]-=sum(M[l,cc]*xt[cc] for cc in range(8))
+        for s in range(steps-1,-1,-1):
+            pk=fbx+s; act=mine&(s<fwx)
+            src=np.where(act,pk,lanes); xk=(y*myinv)[src]
+            ynew=y.copy()
+            for l in range(NP):
+                if act[l] and l==pk[l]: ynew[l]=xk[l]
+                if act[l] and l<pk[l]: ynew[l]=y[l]-Lc[lc0+l-fbx[l],pk[l]]*xk[l]
+            y=ynew
     return np.abs(y[:dof]-ref).max()
 
 
