@@ -1,8 +1,9 @@
-"""Enums, robot names, default config lookup, operator->MANO frames.
+"""Names shared by the whole package: robots, retargeting types, hand sides, the operator -> MANO frame change and the
+lookup of the packaged default configurations.
 
-API mirror of src/dex_retargeting/constants.py:7-87 (reference).  The default configuration files
-are looked up under `dex_retargeting_b200/configs/{teleop,offline}/` (same file names as the
-reference package) -- or under the directory named by $DEX_RETARGETING_CONFIG_DIR.
+Public names and values are those of src/dex_retargeting/constants.py:7-87 (user code imports them); the default
+configuration files live under `dex_retargeting_b200/configs/{teleop,offline}/` with the reference package's file names, or
+under the directory named by $DEX_RETARGETING_CONFIG_DIR.
 """
 import enum
 import os
@@ -11,41 +12,30 @@ from typing import Optional
 
 import numpy as np
 
-OPERATOR2MANO_RIGHT = np.array([[0, 0, -1], [-1, 0, 0], [0, 1, 0]])
-OPERATOR2MANO_LEFT = np.array([[0, 0, -1], [1, 0, 0], [0, -1, 0]])
+# members are numbered from 1 in this order, like enum.auto() in the reference
+RobotName = enum.Enum("RobotName", "allegro shadow svh leap ability inspire panda")
+RetargetingType = enum.Enum("RetargetingType", "vector position dexpilot")  # teleop | offline hand-object data | teleop with a finger-closing prior
+HandType = enum.Enum("HandType", "right left")
+
+# file stem of each robot's URDF and configuration files
+_STEMS = dict(allegro="allegro_hand", shadow="shadow_hand", svh="schunk_svh_hand", leap="leap_hand", ability="ability_hand",
+              inspire="inspire_hand", panda="panda_gripper")
+ROBOT_NAME_MAP = {RobotName[name]: stem for name, stem in _STEMS.items()}
+ROBOT_NAMES = list(ROBOT_NAME_MAP)
 
 
-class RobotName(enum.Enum):
-    allegro = enum.auto()
-    shadow = enum.auto()
-    svh = enum.auto()
-    leap = enum.auto()
-    ability = enum.auto()
-    inspire = enum.auto()
-    panda = enum.auto()
+def _signed_permutation(*rows: str) -> np.ndarray:
+    """Rows given as signed axis names ("-z" = the row (0, 0, -1)): integer matrix of a frame change."""
+    m = np.zeros((3, 3), dtype=int)
+    for r, spec in enumerate(rows):
+        m[r, "xyz".index(spec[-1])] = -1 if spec.startswith("-") else 1
+    return m
 
 
-class RetargetingType(enum.Enum):
-    vector = enum.auto()    # teleoperation, no finger closing prior
-    position = enum.auto()  # offline data, hand-object interaction
-    dexpilot = enum.auto()  # teleoperation, finger closing prior
-
-
-class HandType(enum.Enum):
-    right = enum.auto()
-    left = enum.auto()
-
-
-ROBOT_NAME_MAP = {
-    RobotName.allegro: "allegro_hand",
-    RobotName.shadow: "shadow_hand",
-    RobotName.svh: "schunk_svh_hand",
-    RobotName.leap: "leap_hand",
-    RobotName.ability: "ability_hand",
-    RobotName.inspire: "inspire_hand",
-    RobotName.panda: "panda_gripper",
-}
-ROBOT_NAMES = list(ROBOT_NAME_MAP.keys())
+# operator (wrist-frame estimate of the detector) -> MANO convention; the left hand mirrors the y axis of the right one
+OPERATOR2MANO_RIGHT = _signed_permutation("-z", "-x", "+y")
+OPERATOR2MANO_LEFT = _signed_permutation("-z", "+x", "-y")
+OPERATOR2MANO = {HandType.right: OPERATOR2MANO_RIGHT, HandType.left: OPERATOR2MANO_LEFT}
 
 
 def config_root() -> Path:
@@ -54,13 +44,11 @@ def config_root() -> Path:
 
 
 def get_default_config_path(robot_name: RobotName, retargeting_type: RetargetingType, hand_type: HandType) -> Optional[Path]:
-    sub = "offline" if retargeting_type is RetargetingType.position else "teleop"
-    stem = ROBOT_NAME_MAP[robot_name]
-    if "gripper" not in stem:  # grippers have a single, hand-agnostic file
-        stem = f"{stem}_{hand_type.name}"
+    """`<root>/<teleop|offline>/<stem>[_<hand>][_dexpilot].yml`; grippers have one hand-agnostic file per type."""
+    parts = [ROBOT_NAME_MAP[robot_name]]
+    if "gripper" not in parts[0]:
+        parts.append(hand_type.name)
     if retargeting_type is RetargetingType.dexpilot:
-        stem += "_dexpilot"
-    return config_root() / sub / f"{stem}.yml"
-
-
-OPERATOR2MANO = {HandType.right: OPERATOR2MANO_RIGHT, HandType.left: OPERATOR2MANO_LEFT}
+        parts.append("dexpilot")
+    folder = "offline" if retargeting_type is RetargetingType.position else "teleop"
+    return config_root() / folder / ("_".join(parts) + ".yml")

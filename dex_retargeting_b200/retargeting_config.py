@@ -71,75 +71,71 @@ class RetargetingConfig:
     _TYPE = ["vector", "position", "dexpilot"]
     _DEFAULT_URDF_DIR = "./"
 
+    # what each retargeting type needs from the config: required keys, and the shape of target_link_human_indices as a
+    # function of the number of targets (None = optional, DexPilot derives it from the finger count)
+    _SCHEMA = {
+        "vector": dict(label="Vector", required=("target_origin_link_names", "target_task_link_names"),
+                       count=lambda c: len(c.target_origin_link_names), index_shape=lambda m: (2, m)),
+        "position": dict(label="Position", required=("target_link_names",),
+                         count=lambda c: len(c.target_link_names), index_shape=lambda m: (m,)),
+        "dexpilot": dict(label="DexPilot", required=("finger_tip_link_names", "wrist_link_name"), count=None, index_shape=None),
+    }
+
     def __post_init__(self):
-        self.type = self.type.lower()
-        if self.type not in self._TYPE:
+        self.type = str(self.type).lower()
+        schema = self._SCHEMA.get(self.type)
+        if schema is None:
             raise ValueError(f"Retargeting type must be one of {self._TYPE}")
-
-        if self.type == "vector":
-            if self.target_origin_link_names is None or self.target_task_link_names is None:
-                raise ValueError("Vector retargeting requires: target_origin_link_names + target_task_link_names")
-            if len(self.target_task_link_names) != len(self.target_origin_link_names):
-                raise ValueError("Vector retargeting origin and task links dim mismatch")
+        label = schema["label"]
+        absent = [k for k in schema["required"] if getattr(self, k) is None]
+        if absent:
+            raise ValueError(f"{label} retargeting requires: {' + '.join(schema['required'])} (missing: {', '.join(absent)})")
+        if self.type == "vector" and len(self.target_task_link_names) != len(self.target_origin_link_names):
+            raise ValueError("Vector retargeting origin and task links dim mismatch: "
+                             f"{len(self.target_origin_link_names)} origins, {len(self.target_task_link_names)} tasks")
+        if schema["index_shape"] is not None:
             if self.target_link_human_indices is None:
-                raise ValueError("Vector retargeting requires: target_link_human_indices")
-            self.target_link_human_indices = np.asarray(self.target_link_human_indices)
-            if self.target_link_human_indices.shape != (2, len(self.target_origin_link_names)):
-                raise ValueError("Vector retargeting link names and link indices dim mismatch")
-        elif self.type == "position":
-            if self.target_link_names is None:
-                raise ValueError("Position retargeting requires: target_link_names")
-            if self.target_link_human_indices is None:
-                raise ValueError("Position retargeting requires: target_link_human_indices")
-            self.target_link_human_indices = np.asarray(self.target_link_human_indices).squeeze()
-            if self.target_link_human_indices.shape != (len(self.target_link_names),):
-                raise ValueError("Position retargeting link names and link indices dim mismatch")
-        elif self.type == "dexpilot":
-            if self.finger_tip_link_names is None or self.wrist_link_name is None:
-                raise ValueError("Position retargeting requires: finger_tip_link_names + wrist_link_name")
-            if self.target_link_human_indices is not None:
-                print(
-                    "\033[33m",
-                    "Target link human indices is provided in the DexPilot retargeting config, which is uncommon.\n"
-                    "If you do not know exactly how it is used, please leave it to None for default.\n"
-                    "\033[00m",
-                )
+                raise ValueError(f"{label} retargeting requires: target_link_human_indices")
+            idx = np.asarray(self.target_link_human_indices)
+            want = schema["index_shape"](schema["count"](self))
+            if len(want) == 1:
+                idx = idx.squeeze()
+            if idx.shape != want:
+                raise ValueError(f"{label} retargeting link names and link indices dim mismatch: indices {idx.shape}, expected {want}")
+            self.target_link_human_indices = idx
+        elif self.target_link_human_indices is not None:
+            print("\033[33m DexPilot derives target_link_human_indices from the finger count; a config that sets it "
+                  "overrides that default -- leave it out unless the keypoint layout really differs.\033[00m")
+        self.urdf_path = str(self._resolve_robot_file(self.urdf_path))
 
-        urdf_path = Path(self.urdf_path)
-        if not urdf_path.is_absolute():
-            urdf_path = (Path(self._DEFAULT_URDF_DIR) / urdf_path).absolute()
-        if not urdf_path.exists():
-            # robot descriptions exported as flat JSON joint trees (tests/golden/robots) are accepted too
-            alt = (Path(self._DEFAULT_URDF_DIR) / (urdf_path.stem + ".json")).absolute()
-            if not alt.exists():
-                raise ValueError(f"URDF path {urdf_path} does not exist")
-            urdf_path = alt
-        self.urdf_path = str(urdf_path)
+    @classmethod
+    def _resolve_robot_file(cls, name: Union[str, Path]) -> Path:
+        """Absolute path of the robot description: as given, else under the default URDF directory, else the flat JSON
+        joint tree of the same stem there (tests/golden/robots)."""
+        base = Path(cls._DEFAULT_URDF_DIR)
+        path = Path(name)
+        for cand in (path if path.is_absolute() else (base / path).absolute(), (base / (path.stem + ".json")).absolute()):
+            if cand.exists():
+                return cand
+        raise ValueError(f"URDF path {path if path.is_absolute() else (base / path).absolute()} does not exist")
 
     @classmethod
     def set_default_urdf_dir(cls, urdf_dir: Union[str, Path]):
-        path = Path(urdf_dir)
-        if not path.exists():
+        if not Path(urdf_dir).exists():
             raise ValueError(f"URDF dir {urdf_dir} not exists.")
         cls._DEFAULT_URDF_DIR = urdf_dir
 
     @classmethod
     def load_from_file(cls, config_path: Union[str, Path], override: Optional[Dict] = None):
-        path = Path(config_path)
-        if not path.is_absolute():
-            path = path.absolute()
-        with path.open("r") as f:
-            cfg = yaml.safe_load(f)["retargeting"]
-        return cls.from_dict(cfg, override)
+        with Path(config_path).absolute().open("r") as f:
+            return cls.from_dict(yaml.safe_load(f)["retargeting"], override)
 
     @classmethod
     def from_dict(cls, cfg: Dict[str, Any], override: Optional[Dict] = None):
-        cfg = dict(cfg)
-        if cfg.get("target_link_human_indices") is not None:
-            cfg["target_link_human_indices"] = np.array(cfg["target_link_human_indices"])
-        if override is not None:
-            cfg.update(override)
-        return RetargetingConfig(**cfg)
+        merged = {**cfg, **(override or {})}
+        if merged.get("target_link_human_indices") is not None:
+            merged["target_link_human_indices"] = np.array(merged["target_link_human_indices"])
+        return cls(**merged)
 
     def build(self, device: Optional[int] = None) -> SeqRetargeting:
         from .optimizer import DexPilotOptimizer, PositionOptimizer, VectorOptimizer
@@ -147,43 +143,31 @@ class RetargetingConfig:
         model = KinematicModel.load(self.urdf_path, add_dummy_free_joints=self.add_dummy_free_joint)
         robot = RobotWrapper(model)
 
-        # the 6 dummy joints are optimised too
+        # with a free-flying base the six dummy joints are optimised as well (retargeting_config.py:190-191)
         if self.add_dummy_free_joint and self.target_joint_names is not None:
             self.target_joint_names = DUMMY_JOINT_NAMES + self.target_joint_names
-        joint_names = self.target_joint_names if self.target_joint_names is not None else robot.dof_joint_names
+        joints = robot.dof_joint_names if self.target_joint_names is None else self.target_joint_names
 
+        common = dict(target_link_human_indices=self.target_link_human_indices, device=device)
+        loss = dict(norm_delta=self.normal_delta, huber_delta=self.huber_delta)
         if self.type == "position":
-            optimizer = PositionOptimizer(
-                robot, joint_names, target_link_names=self.target_link_names,
-                target_link_human_indices=self.target_link_human_indices,
-                norm_delta=self.normal_delta, huber_delta=self.huber_delta, device=device,
-            )
+            optimizer = PositionOptimizer(robot, joints, target_link_names=self.target_link_names, **loss, **common)
         elif self.type == "vector":
-            optimizer = VectorOptimizer(
-                robot, joint_names, target_origin_link_names=self.target_origin_link_names,
-                target_task_link_names=self.target_task_link_names,
-                target_link_human_indices=self.target_link_human_indices, scaling=self.scaling_factor,
-                norm_delta=self.normal_delta, huber_delta=self.huber_delta, device=device,
-            )
-        elif self.type == "dexpilot":
-            optimizer = DexPilotOptimizer(
-                robot, joint_names, finger_tip_link_names=self.finger_tip_link_names,
-                wrist_link_name=self.wrist_link_name, target_link_human_indices=self.target_link_human_indices,
-                scaling=self.scaling_factor, project_dist=self.project_dist, escape_dist=self.escape_dist,
-                device=device,
-            )
-        else:
-            raise RuntimeError()
+            optimizer = VectorOptimizer(robot, joints, target_origin_link_names=self.target_origin_link_names,
+                                        target_task_link_names=self.target_task_link_names, scaling=self.scaling_factor,
+                                        **loss, **common)
+        else:  # dexpilot: huber_delta / normal_delta are NOT forwarded (retargeting_config.py:218-228)
+            optimizer = DexPilotOptimizer(robot, joints, finger_tip_link_names=self.finger_tip_link_names,
+                                          wrist_link_name=self.wrist_link_name, scaling=self.scaling_factor,
+                                          project_dist=self.project_dist, escape_dist=self.escape_dist, **common)
 
-        lp_filter = LPFilter(self.low_pass_alpha) if 0 <= self.low_pass_alpha <= 1 else None
-
-        has_mimic, source_names, mimic_names, multipliers, offsets = parse_mimic_joint(model)
+        has_mimic, sources, mimics, multipliers, offsets = parse_mimic_joint(model)
         if has_mimic and not self.ignore_mimic_joint:
             optimizer.set_kinematic_adaptor(MimicJointKinematicAdaptor(
-                robot, target_joint_names=joint_names, source_joint_names=source_names,
-                mimic_joint_names=mimic_names, multipliers=multipliers, offsets=offsets,
-            ))
-        return SeqRetargeting(optimizer, has_joint_limits=self.has_joint_limits, lp_filter=lp_filter)
+                robot, target_joint_names=joints, source_joint_names=sources, mimic_joint_names=mimics,
+                multipliers=multipliers, offsets=offsets))
+        smoothing = LPFilter(self.low_pass_alpha) if 0 <= self.low_pass_alpha <= 1 else None
+        return SeqRetargeting(optimizer, has_joint_limits=self.has_joint_limits, lp_filter=smoothing)
 
 
 def get_retargeting_config(config_path: Union[str, Path]) -> RetargetingConfig:
