@@ -16,6 +16,7 @@ There is no CPU fallback: without the CUDA library / a GPU these calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from abc import abstractmethod
 from typing import List, Optional
 
@@ -103,7 +104,8 @@ class Optimizer:
         self._engine: Optional[_Engine] = None
         # solver knobs that have no counterpart in the reference
         self.max_iters = 64
-        self.step_tol = 1e-5
+        # DEXR_STEP_TOL overrides the default stopping step for A/B runs; the attribute stays settable
+        self.step_tol = float(os.environ.get("DEXR_STEP_TOL", 1e-5))
         self.lambda0 = 1e-2
 
     # ---------------------------------------------------------------- reference API

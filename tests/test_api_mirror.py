@@ -190,3 +190,16 @@ def test_packaged_default_configs_load_with_fixture_robots():
     seq = RetargetingConfig.load_from_file(get_default_config_path(RobotName.allegro, RetargetingType.vector, HandType.right),
                                            override=dict(scaling_factor=1.0, low_pass_alpha=0)).build()
     assert seq.optimizer.scaling == 1.0 and seq.filter.alpha == 0
+
+
+def test_step_tol_default_and_env_override(monkeypatch):
+    """`Optimizer.step_tol` defaults to 1e-5; DEXR_STEP_TOL (A/B switch) changes the default of
+    optimizers constructed afterwards and reaches the launch parameters."""
+    RetargetingConfig.set_default_urdf_dir(str(ROBOTS))
+    path = get_default_config_path(RobotName.allegro, RetargetingType.vector, HandType.right)
+    monkeypatch.delenv("DEXR_STEP_TOL", raising=False)
+    opt = RetargetingConfig.load_from_file(path).build().optimizer
+    assert opt.step_tol == 1e-5 and abs(opt.params().tol - 1e-5) < 1e-12
+    monkeypatch.setenv("DEXR_STEP_TOL", "1e-4")
+    opt = RetargetingConfig.load_from_file(path).build().optimizer
+    assert opt.step_tol == 1e-4 and abs(opt.params().tol - 1e-4) < 1e-11

@@ -1,0 +1,28 @@
+#!/usr/bin/env bash
+# A/B of the opt-in kernel / solver variants on ONE B200 (run under gpurun; writes gpurun_out/ab/).
+#   gpurun --timeout 900 -- 'bash tools/ab_variants.sh'
+# Each variant: the bench line (device arm + e2e, no CPU baseline), then -- only if the variant changes results --
+# the GPU parity tests.  Nothing here is a bench value of record: it picks what to make the default.
+set -u
+out=gpurun_out/ab
+mkdir -p "$out"
+run() {  # name, env assignments...
+  local name=$1; shift
+  echo "== $name: $*"
+  env "$@" python bench.py --steps 20 --warmup 3 --no-cpu-baseline > "$out/bench_$name.json" 2> "$out/bench_$name.err"
+  tail -c 600 "$out/bench_$name.json"; echo
+}
+run base            DEXR_NOP=1
+run g16w20          DEXR_G16_WARPS=20
+run g16w24          DEXR_G16_WARPS=24
+run tol1e-4         DEXR_STEP_TOL=1e-4
+run g16w20_tol1e-4  DEXR_G16_WARPS=20 DEXR_STEP_TOL=1e-4
+run g16w24_tol1e-4  DEXR_G16_WARPS=24 DEXR_STEP_TOL=1e-4
+# the occupancy variants run the same arithmetic (bit-identical results expected): the parity file that checks
+# determinism across entry points is enough; the stopping threshold changes results: the whole GPU suite
+for v in "DEXR_G16_WARPS=20" "DEXR_G16_WARPS=24"; do
+  env $v timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > "$out/pytest_${v#*=}.log" 2>&1; echo "$v parity exit $?"
+done
+env DEXR_STEP_TOL=1e-4 timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_tol1e-4.log" 2>&1; echo "tol 1e-4 suite exit $?"
+env DEXR_STEP_TOL=1e-4 python tools/bench_configs.py --out "$out/configs_tol1e-4.md" > "$out/configs_tol1e-4.jsonl" 2>&1
+python tools/bench_configs.py --out "$out/configs_base.md" > "$out/configs_base.jsonl" 2>&1
