@@ -24,24 +24,39 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
 
 
-def build_library(force: bool = False, verbose: bool = True) -> Path:
-    if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
-        return OUT
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(OUT), str(SRC)]
+# Experimental builds (csrc/dexr_kernels.cuh, "Experiment switches"): one library per entry under variants/, loaded with
+# DEXR_LIBRARY=<path>.  They are A/B material for tools/ab_variants.sh, never the default.
+VARIANTS = {
+    "smallcode": ["-DDEXR_EXP_SMALLCODE"],
+    "fastsincos": ["-DDEXR_EXP_FASTSINCOS"],
+    "smallcode_fastsincos": ["-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_FASTSINCOS"],
+}
+
+
+def build_library(force: bool = False, verbose: bool = True, variant: str = "") -> Path:
+    out = PKG / "variants" / f"libdexr_{variant}.so" if variant else OUT
+    log_path = PKG / "csrc" / (f"build_{variant}.log" if variant else "build.log")
+    if not force and out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
+        return out
+    out.parent.mkdir(exist_ok=True)
+    cmd = [find_nvcc(), *NVCC_FLAGS, *(VARIANTS[variant] if variant else []), "-o", str(out), str(SRC)]
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = (res.stdout or "") + (res.stderr or "")
-    (PKG / "csrc" / "build.log").write_text(log)
+    log_path.write_text(log)
     if res.returncode != 0:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libdexr.so")
+        raise RuntimeError(f"nvcc failed building {out.name}")
     if verbose:
         for line in log.splitlines():
             if "registers" in line or "spill" in line:
                 print(line)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     build_library(force="--force" in sys.argv)
+    if "--variants" in sys.argv:
+        for name in VARIANTS:
+            build_library(force="--force" in sys.argv, variant=name)

@@ -34,6 +34,17 @@
 
 #include "../../include/dexr.h"
 
+// Experiment switches (compile time; `python -m dex_retargeting_b200.build --variants` builds one library per switch
+// next to the default one, selected at run time with DEXR_LIBRARY).  The default build defines none of them.
+//   DEXR_EXP_SMALLCODE   keep the short run-time loops of the FK / link placement rolled (smaller LM loop body in
+//                        the instruction cache; the compiler otherwise unrolls them 3-4x with remainder loops)
+//   DEXR_EXP_FASTSINCOS  MUFU sine / cosine (__sincosf, abs. error ~5e-7 on [-pi, pi]) instead of sincosf
+#ifdef DEXR_EXP_SMALLCODE
+#define DEXR_ROLL _Pragma("unroll 1")
+#else
+#define DEXR_ROLL
+#endif
+
 namespace dexr {
 
 // The whole dynamic shared memory of a CTA.  Declared once at namespace scope so that every access below is
@@ -287,7 +298,11 @@ struct Solver {
   // Forward kinematics (robot_wrapper.py:82-83 [pinocchio forwardKinematics]) by pointer jumping.
   __device__ __forceinline__ void fk(float qv, float* Ro, float* po) const {
     float s, c;
+#ifdef DEXR_EXP_FASTSINCOS
+    __sincosf(qv, &s, &c);
+#else
     sincosf(qv, &s, &c);
+#endif
     const float omc = 1.0f - c;
     const bool rev = jtype == 0;
     float w[9];
@@ -300,6 +315,7 @@ struct Solver {
 #pragma unroll
     for (int i = 0; i < 3; ++i) po[i] = rev ? w[i] : fmaf(qv, w[3 + i], w[i]);
     const int rounds = dm.n_rounds;
+    DEXR_ROLL
     for (int r = 0; r < rounds; ++r) {
       const int src = (jump >> (6 * r)) & 63;
       const bool has = src != 63;
@@ -331,6 +347,7 @@ struct Solver {
   __device__ __forceinline__ void write_links(const float* Rw, const float* pw, int b) const {
     float4* out = lp(b);
     const int rounds = ST().own_rounds;
+    DEXR_ROLL
     for (int r = 0; r < rounds; ++r) {
       const float4 o = ST().lane_link[r][l];
       const int slot = __float_as_int(o.w);
@@ -342,6 +359,7 @@ struct Solver {
   }
   __device__ __forceinline__ void write_world_links() const {
     const int L = dm.n_links;
+    DEXR_ROLL
     for (int k = l; k < L; k += G) {
       const float4 o = ST().link_off[k];
       if (__float_as_int(o.w) < 0) {
