@@ -30,6 +30,8 @@ VARIANTS = {
     "smallcode": ["-DDEXR_EXP_SMALLCODE"],
     "fastsincos": ["-DDEXR_EXP_FASTSINCOS"],
     "smallcode_fastsincos": ["-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_FASTSINCOS"],
+    "mergedres": ["-DDEXR_EXP_MERGEDRES"],
+    "mergedres_smallcode": ["-DDEXR_EXP_MERGEDRES", "-DDEXR_EXP_SMALLCODE"],
 }
 
 

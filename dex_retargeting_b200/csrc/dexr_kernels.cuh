@@ -39,6 +39,10 @@
 //   DEXR_EXP_SMALLCODE   keep the short run-time loops of the FK / link placement rolled (smaller LM loop body in
 //                        the instruction cache; the compiler otherwise unrolls them 3-4x with remainder loops)
 //   DEXR_EXP_FASTSINCOS  MUFU sine / cosine (__sincosf, abs. error ~5e-7 on [-pi, pi]) instead of sincosf
+//   DEXR_EXP_MERGEDRES   block mode only: every residual touches the joints of ONE lane window (validated with the table),
+//                        so each window walks its own residual list in the same pass instead of all lanes walking all
+//                        n_res residuals (Allegro / LEAP vector: 1 trip instead of 4).  Contributions a lane no longer
+//                        visits were exact zeros: same results up to the sign of zero
 #ifdef DEXR_EXP_SMALLCODE
 #define DEXR_ROLL _Pragma("unroll 1")
 #else
@@ -161,6 +165,12 @@ struct SharedTable {
   int group_count[DEXR_MAX_LANES];
   int group_lane[DEXR_MAX_LANES][DEXR_MAX_GROUP];
   float group_mult[DEXR_MAX_LANES][DEXR_MAX_GROUP];
+#ifdef DEXR_EXP_MERGEDRES
+  // block mode: residuals by lane window (window = first joint touched / block_width; a residual that touches no
+  // joint sits in window 0 so that it still counts for the residual maximum); -1 pads the lists to win_trips
+  int win_res[DEXR_MAX_LANES / 4][DEXR_MAX_RES];
+  int win_trips;
+#endif
 };
 
 __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __restrict__ tb) {
@@ -199,6 +209,23 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
         mx = n > mx ? n : mx;
       }
       st.own_rounds = mx > DEXR_MAX_LINKS_PER_LANE ? DEXR_MAX_LINKS_PER_LANE : mx;
+#ifdef DEXR_EXP_MERGEDRES
+      int trips = 0;
+      if (tb->block_width > 0) {
+        for (int w = 0; w < DEXR_MAX_LANES / 4; ++w) {
+          int n = 0;
+          for (int k = 0; k < tb->n_res; ++k) {
+            const uint32_t msk = tb->link_anc_mask[tb->res_task[k]] |
+                                 (tb->res_origin[k] >= 0 ? tb->link_anc_mask[tb->res_origin[k]] : 0u);
+            const int win = msk ? (__ffs(msk) - 1) / tb->block_width : 0;
+            if (win == w) st.win_res[w][n++] = k;
+          }
+          trips = n > trips ? n : trips;
+          for (int k = n; k < DEXR_MAX_RES; ++k) st.win_res[w][k] = -1;
+        }
+      }
+      st.win_trips = trips;
+#endif
     }
     for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
       st.group_lane[i][f] = tb->group_lane[i][f];
@@ -543,11 +570,29 @@ struct Solver {
       const int cb = dense ? 0 : (l & ~(BW - 1));
       const float4* lpc = lp(cur);
       float rmax = 0.f;
-      for (int k = 0; k < m; ++k) {
+#ifdef DEXR_EXP_MERGEDRES
+      constexpr bool merged = BW > 0;
+#else
+      constexpr bool merged = false;
+#endif
+      int trips = m;
+#ifdef DEXR_EXP_MERGEDRES
+      if constexpr (merged) trips = ST().win_trips;
+#endif
+      for (int kk = 0; kk < trips; ++kk) {
+        int k = kk;
+        bool on = true;  // merged mode: false on the lanes of a window whose residual list is exhausted
+#ifdef DEXR_EXP_MERGEDRES
+        if constexpr (merged) {
+          const int kw = ST().win_res[l / (BW > 0 ? BW : 1)][kk];
+          on = kw >= 0;
+          k = on ? kw : 0;
+        }
+#endif
         const int ti = ST().res_task[k], oi = ST().res_origin[k];
         const float4 T = fr()[k];
         const float4 pt = lpc[ti];
-        const uint32_t mt = ST().link_anc[ti];
+        const uint32_t mt = on ? ST().link_anc[ti] : 0u;
         float rx = pt.x - T.x, ry = pt.y - T.y, rz = pt.z - T.z;
         float j0 = 0.f, j1 = 0.f, j2 = 0.f;
         if ((mt >> l) & 1u) {
@@ -559,7 +604,7 @@ struct Solver {
         uint32_t mo = 0u;
         if (oi >= 0) {
           const float4 po = lpc[oi];
-          mo = ST().link_anc[oi];
+          mo = on ? ST().link_anc[oi] : 0u;
           rx -= po.x; ry -= po.y; rz -= po.z;
           if ((mo >> l) & 1u) {
             if (rev) {
@@ -574,7 +619,7 @@ struct Solver {
           // per-coordinate Huber: exact curvature is 0 beyond beta; the majoriser 1/max(|r|, beta) is
           // used throughout (identical inside the quadratic zone)
           const float ax_ = fabsf(rx), ay_ = fabsf(ry), az_ = fabsf(rz);
-          rmax = fmaxf(rmax, fmaxf(ax_, fmaxf(ay_, az_)));
+          rmax = on ? fmaxf(rmax, fmaxf(ax_, fmaxf(ay_, az_))) : rmax;
           // 1/beta exactly inside the quadratic zone; beyond it the fast reciprocal (<= 2 ulp) is plenty: it only
           // scales a unit-magnitude gradient component and the majoriser curvature
           const float wx = ax_ < beta ? inv_beta : __fdividef(1.0f, ax_);
@@ -584,7 +629,7 @@ struct Solver {
           y0 = T.w * wx * j0; y1 = T.w * wy * j1; y2 = T.w * wz * j2;
         } else {
           const float d = sqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
-          rmax = fmaxf(rmax, d);
+          rmax = on ? fmaxf(rmax, d) : rmax;
           const bool quad = d < beta;
           const float invd = d > 0.f ? __frcp_rn(d) : 0.f;
           const float ux = rx * invd, uy = ry * invd, uz = rz * invd;
@@ -597,7 +642,7 @@ struct Solver {
         }
         g = fmaf(j0, gx, fmaf(j1, gy, fmaf(j2, gz, g)));
         t0 += j1 * gz - j2 * gy; t1 += j2 * gx - j0 * gz; t2 += j0 * gy - j1 * gx;
-        const int b = k & 1;
+        const int b = kk & 1;
         jbuf(b, 0)[l] = j0; jbuf(b, 1)[l] = j1; jbuf(b, 2)[l] = j2;
         __syncwarp();
         const uint32_t cols = mt | mo;
@@ -639,6 +684,7 @@ struct Solver {
           }
         }
       }
+      if constexpr (merged) rmax = gmax<G>(rmax);  // every window saw only its own residuals
       if constexpr (AR) {  // the aligned trunk chunks also swept columns ar_t..7 (finger lanes): not trunk couplings
 #pragma unroll
         for (int c = 0; c < 8; ++c) H[8 + c] = c < ar_t ? H[8 + c] : 0.f;
