@@ -35,7 +35,7 @@ def main(path, kernel, call_line):
         if m.group(2) == "WARPSYNC":
             break
         total += 1
-        key = next((("solve", l) for f, l, inf, inl in stack if inf == "dexr.cu" and inl == call_line and f == "dexr_kernels.cuh"), None)
+        key = next((("solve", l) for f, l, inf, inl in stack if inl == call_line and f == "dexr_kernels.cuh"), None)
         if key is None:
             key = stack[-1][:2] if stack else ("?", 0)
         by[key] += 1
