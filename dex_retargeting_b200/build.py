@@ -30,6 +30,9 @@ VARIANTS = {
     "smallcode": ["-DDEXR_EXP_SMALLCODE"],
     "fastsincos": ["-DDEXR_EXP_FASTSINCOS"],
     "smallcode_fastsincos": ["-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_FASTSINCOS"],
+    "pdfallback": ["-DDEXR_EXP_PDFALLBACK"],
+    "pdfallback_smallcode": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_SMALLCODE"],
+    "all": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_MERGEDRES"],
     "mergedres": ["-DDEXR_EXP_MERGEDRES"],
     "mergedres_smallcode": ["-DDEXR_EXP_MERGEDRES", "-DDEXR_EXP_SMALLCODE"],
 }

@@ -6,6 +6,8 @@ kernel's iteration (tools/lm_prototype.py).  Design-time only: nothing here is a
   python tests/tools/solver_model_probe.py lam   offline/shadow_hand_right 512    # damping-schedule sweep
   python tests/tools/solver_model_probe.py traj  offline/shadow_hand_right 256    # step / error per iteration
   python tests/tools/solver_model_probe.py start offline/shadow_hand_right 256    # Hessian spectrum at the warm start
+  python tests/tools/solver_model_probe.py curv  offline/shadow_hand_right 256 [target noise, m]   # curvature gating rules
+  python tests/tools/solver_model_probe.py stream teleop/allegro_hand_right 200  # same rules, recorded stream, warm starts
 
 Numbers quoted in DESIGN.md section 5c come from these commands.
 """
@@ -97,5 +99,49 @@ def cmd_start(key, B):
           f"Gauss-Newton + regulariser: min {np.median(evgn[:, 0]):.3e}, max {np.median(evgn[:, -1]):.3e}")
 
 
+CURV_RULES = [("kernel", {}), ("skip first 1", dict(curv_skip_first=1)), ("skip first 2", dict(curv_skip_first=2)),
+              ("after step<.05", dict(curv_after_small=0.05)), ("pd fallback", dict(curv_pd_fallback=True))]
+
+
+def _compare_rules(P, o, target, weights, fx, x0, skip=0):
+    P64 = LP.ProtoProblem(o, np.float64)
+    w64 = None if weights is None else weights.astype(np.float64)
+    xr, _, Fr, _ = solve(P64, target.astype(np.float64), w64, fx.astype(np.float64), x0.astype(np.float64), max_iter=100, lam0=1e-2, tol=1e-9)
+    for name, kw in CURV_RULES:
+        x, it, F, s = solve(P, target, weights, fx, x0, max_iter=64, lam0=1e-2, tol=1e-5, **kw)
+        d = np.abs(x - xr).max(1)
+        print(f"  {name:15s}: mean iterations {it[skip:].mean():.3f} (max {it[skip:].max()}), solves/frame {s:.3f}, F - F_ref max "
+              f"{np.max(F - Fr):.2e}, |dq|inf p99 {np.percentile(d, 99):.2e}, other basin {(d > 1e-4).mean():.3f}", flush=True)
+
+
+def cmd_curv(key, B, noise=0.0):
+    """When to include the kinematic (FK second derivative) curvature: the kernel's rule (residual below kFarResidual),
+    Gauss-Newton for the first iterations, only after a small accepted step, or always but dropped when the damped
+    Hessian is not positive definite (DEXR_EXP_PDFALLBACK).  `noise`: unreachable targets (std, metres)."""
+    P, o, target, weights, fx, x0 = problem(key, B)
+    target = (target + np.random.RandomState(5).randn(*target.shape) * float(noise)).astype(np.float32)
+    print(key, "bench-style problems, target noise", noise)
+    _compare_rules(P, o, target, weights, fx, x0)
+
+
+def cmd_stream(key, T):
+    """The same rules on the recorded keypoint trajectory, every frame warm-started from the previous frame's solution."""
+    from helpers import keypoint_trajectory
+    o = build_oracle(key)
+    kp = keypoint_trajectory()[:T].astype(np.float32)
+    refs = np.stack([o.ref_from_keypoints(kp[i]) for i in range(T)]).astype(np.float32)
+    assert o.type in ("vector", "position")
+    target = refs * np.float32(o.scaling) if o.type == "vector" else refs
+    weights = np.ones((T, o.m), np.float32) if o.type == "vector" else None
+    P, fx = LP.ProtoProblem(o, np.float32), np.zeros((T, 0), np.float32)
+    x, starts = ((o.lower + o.upper) / 2).astype(np.float32)[None], []
+    for t in range(T):
+        starts.append(x[0].copy())
+        x = solve(P, target[t:t + 1], None if weights is None else weights[t:t + 1], fx[:1], x, max_iter=64, lam0=1e-2, tol=1e-5)[0]
+    print(key, "recorded stream,", T, "frames")
+    _compare_rules(P, o, target, weights, fx, np.array(starts), skip=1)
+
+
 if __name__ == "__main__":
-    {"tol": cmd_tol, "lam": cmd_lam, "traj": cmd_traj, "start": cmd_start}[sys.argv[1]](sys.argv[2], int(sys.argv[3]))
+    cmds = {"tol": cmd_tol, "lam": cmd_lam, "traj": cmd_traj, "start": cmd_start, "curv": cmd_curv, "stream": cmd_stream}
+    cmds[sys.argv[1]](sys.argv[2], int(sys.argv[3]), *sys.argv[4:])

@@ -24,6 +24,8 @@ run merged_small    DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so
 run merged_small_w20 DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so DEXR_G16_WARPS=20
 run merged_small_w24 DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so DEXR_G16_WARPS=24
 run merged_small_tol DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so DEXR_STEP_TOL=1e-4
+run pdfallback      DEXR_LIBRARY=$V/libdexr_pdfallback.so
+run all_three       DEXR_LIBRARY=$V/libdexr_all.so
 run small_w20       DEXR_LIBRARY=$V/libdexr_smallcode.so DEXR_G16_WARPS=20
 run small_w24       DEXR_LIBRARY=$V/libdexr_smallcode.so DEXR_G16_WARPS=24
 run g16w20          DEXR_G16_WARPS=20
@@ -39,6 +41,11 @@ done
 # smallcode is the same arithmetic in the same order (bit-identical expected); fastsincos changes the FK by ~5e-7
 env DEXR_LIBRARY=$V/libdexr_smallcode.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_smallcode.log" 2>&1; echo "smallcode suite exit $?"
 env DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_mergedres_smallcode.log" 2>&1; echo "mergedres_smallcode suite exit $?"
+# pdfallback changes the iteration path (results within the solver tolerance, not bit-identical): whole suite + all configs
+env DEXR_LIBRARY=$V/libdexr_pdfallback.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_pdfallback.log" 2>&1; echo "pdfallback suite exit $?"
+env DEXR_LIBRARY=$V/libdexr_pdfallback.so python tools/bench_configs.py --out "$out/configs_pdfallback.md" > "$out/configs_pdfallback.jsonl" 2>&1
+env DEXR_LIBRARY=$V/libdexr_all.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_all.log" 2>&1; echo "all-three suite exit $?"
+env DEXR_LIBRARY=$V/libdexr_all.so python tools/bench_configs.py --out "$out/configs_all.md" > "$out/configs_all.jsonl" 2>&1
 env DEXR_LIBRARY=$V/libdexr_fastsincos.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_fastsincos.log" 2>&1; echo "fastsincos suite exit $?"
 env DEXR_LIBRARY=$V/libdexr_smallcode.so python tools/bench_configs.py --out "$out/configs_smallcode.md" > "$out/configs_smallcode.jsonl" 2>&1
 env DEXR_STEP_TOL=1e-4 timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_tol1e-4.log" 2>&1; echo "tol 1e-4 suite exit $?"

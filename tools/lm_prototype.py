@@ -121,7 +121,7 @@ def huber(d, beta):
 
 def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, tol=1e-6, ggn=True, lam0=1e-3,
                 verbose=False, newton=False, hybrid=False, near=0.1, curv_far=True, pos_majorise=False, start_exact=False,
-                chord=0.0, extrap=False):
+                chord=0.0, extrap=False, curv_skip_first=0, curv_pd_fallback=False, curv_after_small=0.0):
     """target [B,m,3] (already scaled / projected), weights [B,m] or None (position)."""
     o, dt = P.o, P.dt
     B, n = x0.shape
@@ -158,6 +158,8 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
     r = residuals(pos)
     F = cost(r, x)
     x_before_last = x.copy()
+    curv_armed = np.zeros(B, bool)
+    H_nocurv = None
     for it in range(max_iter):
         x_prev = x.copy()
         # gradient / GGN Hessian at x
@@ -196,7 +198,13 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
                     gpos[:, o.origin_sel[k]] -= gv[:, k]
             rmax = np.abs(r).reshape(B, -1).max(1) if o.type == 'position' else np.linalg.norm(r, axis=2).max(1)
             cw = np.ones(B, dt) if (curv_far or not hybrid) else (rmax < RFAR).astype(dt)
-            H = H + P.curvature(gpos) * cw[:, None, None]
+            if it < curv_skip_first:      # experiment: Gauss-Newton model for the first iterations
+                cw = cw * 0
+            if curv_after_small > 0:      # experiment: kinematic curvature only after an accepted step below this size
+                cw = cw * curv_armed.astype(dt)
+            Hcurv = P.curvature(gpos) * cw[:, None, None]
+            H_nocurv = H + 2 * nd * np.eye(n, dtype=dt)[None]
+            H = H + Hcurv
         g = g + 2 * nd * (x - last)
         H = H + 2 * nd * np.eye(n, dtype=dt)[None]
         act = ((x <= lo) & (g > 0)) | ((x >= hi) & (g < 0))
@@ -237,6 +245,12 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             A = H_f.copy()
             A[:, np.arange(n), np.arange(n)] += lam[:, None] * diag
             pd = np.linalg.eigvalsh(A.astype(np.float64)).min(1) > 0
+            if curv_pd_fallback and newton and H_nocurv is not None and (~pd).any():
+                # experiment: indefinite with the kinematic curvature -> same damping on the PSD model without it
+                A2 = H_nocurv * (~act)[:, :, None] * (~act)[:, None, :]
+                A2[:, np.arange(n), np.arange(n)] += act.astype(dt) + lam[:, None] * diag
+                A = np.where(pd[:, None, None], A, A2)
+                pd = np.linalg.eigvalsh(A.astype(np.float64)).min(1) > 0
             if False and hybrid and start_exact and trial == 0:
                 switch = exact & ~pd & ~accepted
                 accepted = accepted | switch
@@ -278,6 +292,7 @@ def solve_batch(P: ProtoProblem, target, weights, fixed, x0, last, max_iter=40, 
             accepted |= upd
             if accepted.all():
                 break
+        curv_armed = accepted & ~chord_now & (np.abs(x - x_prev).max(1) < curv_after_small)
         stuck = ~accepted & ~chord_now
         if hybrid:
             done |= stuck & ~exact  # the majoriser model failed too: at the (numerical) minimum
