@@ -1,53 +1,53 @@
 #!/usr/bin/env bash
 # A/B of the opt-in kernel / solver variants on ONE B200 (run under gpurun; writes gpurun_out/ab/).
-#   gpurun --timeout 900 -- 'bash tools/ab_variants.sh'
-# Each variant: the bench line (device arm + e2e, no CPU baseline), then -- only if the variant changes results --
-# the GPU parity tests.  Nothing here is a bench value of record: it picks what to make the default.
+#   gpurun --timeout 1200 -- 'bash tools/ab_variants.sh bench'                 # bench line per variant (~1 min each)
+#   gpurun --timeout 1500 -- 'bash tools/ab_variants.sh verify all'            # GPU suite + all configs under ONE variant
+#   gpurun --timeout 900  -- 'bash tools/ab_variants.sh verify "" DEXR_STEP_TOL=1e-4'   # default library + an env switch
+# Variants: libraries built by `python -m dex_retargeting_b200.build --variants` (compile-time switches, see
+# csrc/dexr_kernels.cuh "Experiment switches") selected with DEXR_LIBRARY, and the run-time switches DEXR_G16_WARPS /
+# DEXR_STEP_TOL.  Nothing printed here is a bench value of record: it picks what becomes the default.
 set -u
 out=gpurun_out/ab
 mkdir -p "$out"
-run() {  # name, env assignments...
-  local name=$1; shift
-  echo "== $name: $*"
-  env "$@" python bench.py --steps 20 --warmup 3 --no-cpu-baseline > "$out/bench_$name.json" 2> "$out/bench_$name.err"
-  tail -c 600 "$out/bench_$name.json"; echo
-}
-# compile-time experiments (dexr_kernels.cuh "Experiment switches"); built here if the snapshot did not bring them
-python -m dex_retargeting_b200.build --variants > "$out/build_variants.log" 2>&1 || echo "variant build failed"
+python -m dex_retargeting_b200.build --variants > "$out/build_variants.log" 2>&1 || echo "variant build failed (see $out/build_variants.log)"
 V=$PWD/dex_retargeting_b200/variants
-run base            DEXR_NOP=1
-run smallcode       DEXR_LIBRARY=$V/libdexr_smallcode.so
-run fastsincos      DEXR_LIBRARY=$V/libdexr_fastsincos.so
-run small_fast      DEXR_LIBRARY=$V/libdexr_smallcode_fastsincos.so
-run mergedres       DEXR_LIBRARY=$V/libdexr_mergedres.so
-run merged_small    DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so
-run merged_small_w20 DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so DEXR_G16_WARPS=20
-run merged_small_w24 DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so DEXR_G16_WARPS=24
-run merged_small_tol DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so DEXR_STEP_TOL=1e-4
-run pdfallback      DEXR_LIBRARY=$V/libdexr_pdfallback.so
-run all_three       DEXR_LIBRARY=$V/libdexr_all.so
-run small_w20       DEXR_LIBRARY=$V/libdexr_smallcode.so DEXR_G16_WARPS=20
-run small_w24       DEXR_LIBRARY=$V/libdexr_smallcode.so DEXR_G16_WARPS=24
-run g16w20          DEXR_G16_WARPS=20
-run g16w24          DEXR_G16_WARPS=24
-run tol1e-4         DEXR_STEP_TOL=1e-4
-run g16w20_tol1e-4  DEXR_G16_WARPS=20 DEXR_STEP_TOL=1e-4
-run g16w24_tol1e-4  DEXR_G16_WARPS=24 DEXR_STEP_TOL=1e-4
-# the occupancy variants run the same arithmetic (bit-identical results expected): the parity file that checks
-# determinism across entry points is enough; the stopping threshold changes results: the whole GPU suite
-for v in "DEXR_G16_WARPS=20" "DEXR_G16_WARPS=24"; do
-  env $v timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > "$out/pytest_${v#*=}.log" 2>&1; echo "$v parity exit $?"
-done
-# smallcode is the same arithmetic in the same order (bit-identical expected); fastsincos changes the FK by ~5e-7
-env DEXR_LIBRARY=$V/libdexr_smallcode.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_smallcode.log" 2>&1; echo "smallcode suite exit $?"
-env DEXR_LIBRARY=$V/libdexr_mergedres_smallcode.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_mergedres_smallcode.log" 2>&1; echo "mergedres_smallcode suite exit $?"
-# pdfallback changes the iteration path (results within the solver tolerance, not bit-identical): whole suite + all configs
-env DEXR_LIBRARY=$V/libdexr_pdfallback.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_pdfallback.log" 2>&1; echo "pdfallback suite exit $?"
-env DEXR_LIBRARY=$V/libdexr_pdfallback.so python tools/bench_configs.py --out "$out/configs_pdfallback.md" > "$out/configs_pdfallback.jsonl" 2>&1
-env DEXR_LIBRARY=$V/libdexr_all.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_all.log" 2>&1; echo "all-three suite exit $?"
-env DEXR_LIBRARY=$V/libdexr_all.so python tools/bench_configs.py --out "$out/configs_all.md" > "$out/configs_all.jsonl" 2>&1
-env DEXR_LIBRARY=$V/libdexr_fastsincos.so timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_fastsincos.log" 2>&1; echo "fastsincos suite exit $?"
-env DEXR_LIBRARY=$V/libdexr_smallcode.so python tools/bench_configs.py --out "$out/configs_smallcode.md" > "$out/configs_smallcode.jsonl" 2>&1
-env DEXR_STEP_TOL=1e-4 timeout 1500 python -m pytest tests -x -q -m gpu > "$out/pytest_tol1e-4.log" 2>&1; echo "tol 1e-4 suite exit $?"
-env DEXR_STEP_TOL=1e-4 python tools/bench_configs.py --out "$out/configs_tol1e-4.md" > "$out/configs_tol1e-4.jsonl" 2>&1
-python tools/bench_configs.py --out "$out/configs_base.md" > "$out/configs_base.jsonl" 2>&1
+lib() { [ -n "$1" ] && echo "DEXR_LIBRARY=$V/libdexr_$1.so" || echo "DEXR_NOP=1"; }
+
+bench_one() {  # name, env assignments...
+  local name=$1; shift
+  env "$@" python bench.py --steps 20 --warmup 3 --no-cpu-baseline > "$out/bench_$name.json" 2> "$out/bench_$name.err"
+  python - "$name" "$out/bench_$name.json" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print(f"{sys.argv[1]:24s} value {d['value']:.4e}  e2e {d['e2e']['value']:.4e}  iterations {d['solver']['mean_iterations']:.3f}  "
+          f"flagged {d['solver']['frames_flagged']}  launch {d['solver']['launch']['block']} thr")
+except Exception as e:
+    print(f"{sys.argv[1]:24s} FAILED: {e}")
+PY
+}
+
+case "${1:-bench}" in
+bench)
+  bench_one base DEXR_NOP=1
+  for v in smallcode fastsincos mergedres mergedres_smallcode pdfallback all; do bench_one "$v" "$(lib $v)"; done
+  for w in 20 24; do
+    bench_one "w$w" DEXR_G16_WARPS=$w
+    bench_one "all_w$w" "$(lib all)" DEXR_G16_WARPS=$w
+  done
+  bench_one tol1e-4 DEXR_STEP_TOL=1e-4
+  bench_one all_tol1e-4 "$(lib all)" DEXR_STEP_TOL=1e-4
+  # Shadow position / DexPilot / streams are where pdfallback matters: the multi-config table under the two libraries
+  python tools/bench_configs.py --out "$out/configs_base.md" > "$out/configs_base.jsonl" 2>&1
+  env "$(lib all)" python tools/bench_configs.py --out "$out/configs_all.md" > "$out/configs_all.jsonl" 2>&1
+  cat "$out/configs_base.md" "$out/configs_all.md"
+  ;;
+verify)
+  v=${2:-}; shift; shift || true
+  tag=${v:-default}$(printf '_%s' "$@" | tr -c 'A-Za-z0-9_.=\n-' '_')
+  env "$(lib "$v")" "$@" timeout 1800 python -m pytest tests -x -q -m gpu > "$out/pytest_$tag.log" 2>&1; echo "GPU suite under $tag: exit $?"; tail -3 "$out/pytest_$tag.log"
+  env "$(lib "$v")" "$@" python tools/bench_configs.py --out "$out/configs_$tag.md" > "$out/configs_$tag.jsonl" 2>&1; cat "$out/configs_$tag.md"
+  bench_one "$tag" "$(lib "$v")" "$@"
+  ;;
+*) echo "usage: $0 bench | verify <variant or ''> [ENV=VALUE ...]"; exit 2 ;;
+esac
