@@ -30,13 +30,22 @@ def problem(key, B, seed=100, dtype=np.float32):
     seq, o = build_product(key), build_oracle(key)
     kp, x0, fixed, _ = synth(seq, B, seed)
     refs = np.stack([o.ref_from_keypoints(kp[i]) for i in range(B)]).astype(dtype)
-    if o.type == "position":
-        target, weights = refs, None
-    else:
-        assert o.type == "vector", "the model takes fixed weights: position / vector configurations only"
-        target, weights = refs * dtype(o.scaling), np.ones((B, o.m), dtype)
+    target, weights = frame_constants(o, refs, dtype, stream=False)
     fx = (fixed if fixed is not None else np.zeros((B, 0))).astype(dtype)
     return LP.ProtoProblem(o, dtype), o, target, weights, fx, x0.astype(dtype)
+
+
+def frame_constants(o, refs, dtype, stream):
+    """Targets and residual weights of every frame (oracle `prepare`: scaling; DexPilot flags, weights, projected targets --
+    flags carried from frame to frame when `stream`, otherwise every frame starts with none set)."""
+    if o.type == "position":
+        return refs.astype(dtype), None
+    tw = []
+    for r in refs:
+        if o.type == "dexpilot" and not stream:
+            o.projected[:] = False
+        tw.append(o.prepare(r, update_state=True))
+    return np.stack([t for t, _ in tw]).astype(dtype), np.stack([w for _, w in tw]).astype(dtype)
 
 
 def solve(P, target, weights, fx, x0, **kw):
@@ -130,9 +139,7 @@ def cmd_stream(key, T):
     o = build_oracle(key)
     kp = keypoint_trajectory()[:T].astype(np.float32)
     refs = np.stack([o.ref_from_keypoints(kp[i]) for i in range(T)]).astype(np.float32)
-    assert o.type in ("vector", "position")
-    target = refs * np.float32(o.scaling) if o.type == "vector" else refs
-    weights = np.ones((T, o.m), np.float32) if o.type == "vector" else None
+    target, weights = frame_constants(o, refs, np.float32, stream=True)
     P, fx = LP.ProtoProblem(o, np.float32), np.zeros((T, 0), np.float32)
     x, starts = ((o.lower + o.upper) / 2).astype(np.float32)[None], []
     for t in range(T):
