@@ -135,7 +135,7 @@ typedef struct dexr_params {
   float eta2;         /* dexpilot, optimizer.py:347 */
   float lp_alpha;     /* sequences only: low-pass alpha; outside [0,1] = no filter */
   float tol;          /* stop when the accepted step is below this (rad / m); default 1e-5 */
-  float lambda0;      /* initial LM damping; default 1e-3 */
+  float lambda0;      /* initial LM damping; default 1e-2 */
   int32_t max_iters;  /* cap on accepted iterations; default 64 */
   int32_t clip_init;  /* 1: clip the warm start to clip_lo/clip_hi first (SeqRetargeting.retarget) */
 } dexr_params_t;
