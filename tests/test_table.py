@@ -185,6 +185,29 @@ def test_block_width_detection():
         assert build_product(key).optimizer.build_table().block_width == bw, key
 
 
+def test_block_mode_residuals_partition_over_lane_windows():
+    """What the merged residual pass (csrc/dexr_kernels.cuh, DEXR_EXP_MERGEDRES / SharedTable::win_res) relies on: in a
+    block-mode table every residual touches joints of exactly one window of `block_width` lanes, so the per-window lists
+    -- window = lowest touched joint // block_width, window 0 for a residual that touches none -- hold every residual once."""
+    seen = 0
+    for key in sorted(configs()):
+        t = build_product(key).optimizer.build_table()
+        if t.block_width == 0:
+            continue
+        seen += 1
+        bw, lists = t.block_width, {}
+        for k in range(t.n_res):
+            m = t.link_anc_mask[t.res_task[k]] | (t.link_anc_mask[t.res_origin[k]] if t.res_origin[k] >= 0 else 0)
+            lo, hi = ((m & -m).bit_length() - 1, m.bit_length() - 1) if m else (0, 0)
+            assert lo // bw == hi // bw, (key, k)
+            lists.setdefault(lo // bw, []).append(k)
+        assert sorted(k for v in lists.values() for k in v) == list(range(t.n_res))
+        assert max(lists) < t.dof // bw
+        if "allegro" in key or "leap" in key:  # one fingertip vector per finger: a single pass instead of four
+            assert max(len(v) for v in lists.values()) == 1 and t.n_res == 4
+    assert seen >= 4
+
+
 def test_library_rejects_inconsistent_block_width():
     import ctypes as C
 
