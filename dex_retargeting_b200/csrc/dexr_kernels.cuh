@@ -44,10 +44,14 @@
 //                        with the positive semi-definite model, instead of multiplying the damping by 10 and refactorising
 //                        until it dominates (fp32 solver model: Shadow position 7.7 -> 5.3 iterations, 10.0 -> 5.3
 //                        factorisations per frame; neutral on warm-started streams and unreachable targets)
-//   DEXR_EXP_MERGEDRES   block mode only: every residual touches the joints of ONE lane window (validated with the table),
-//                        so each window walks its own residual list in the same pass instead of all lanes walking all
-//                        n_res residuals (Allegro / LEAP vector: 1 trip instead of 4).  Contributions a lane no longer
-//                        visits were exact zeros: same results up to the sign of zero
+//   DEXR_EXP_MERGEDRES   a residual only touches the joints above its links; residuals that touch disjoint sets of lane
+//                        slots (block mode: the block_width-lane windows; dense mode: 4-lane chunks) are packed into the
+//                        same pass (greedy, once per CTA: SharedTable::pass_res) and every lane works on the residual of
+//                        its slot, instead of all lanes walking all n_res residuals.  Allegro / LEAP vector: 1 pass
+//                        instead of 4; DexPilot on a palm-fixed hand: the wrist -> tip vectors share a pass and disjoint
+//                        finger pairs share passes (about 4 instead of 10).  Hands with wrist joints above every finger
+//                        get no merging (every residual touches the trunk slot).  The terms a lane no longer visits were
+//                        exact zeros: same sums, up to the sign of zero.  Not used in arrow mode or with mimic joints.
 #ifdef DEXR_EXP_SMALLCODE
 #define DEXR_ROLL _Pragma("unroll 1")
 #else
@@ -171,10 +175,10 @@ struct SharedTable {
   int group_lane[DEXR_MAX_LANES][DEXR_MAX_GROUP];
   float group_mult[DEXR_MAX_LANES][DEXR_MAX_GROUP];
 #ifdef DEXR_EXP_MERGEDRES
-  // block mode: residuals by lane window (window = first joint touched / block_width; a residual that touches no
-  // joint sits in window 0 so that it still counts for the residual maximum); -1 pads the lists to win_trips
-  int win_res[DEXR_MAX_LANES / 4][DEXR_MAX_RES];
-  int win_trips;
+  // pass_res[r][slot]: the residual the lanes of `slot` work on in pass r, -1 = none (slot = lane / block_width in block
+  // mode, lane / 4 in dense mode)
+  int pass_res[DEXR_MAX_RES][DEXR_MAX_LANES / 4];
+  int n_pass;
 #endif
 };
 
@@ -215,21 +219,34 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
       }
       st.own_rounds = mx > DEXR_MAX_LINKS_PER_LANE ? DEXR_MAX_LINKS_PER_LANE : mx;
 #ifdef DEXR_EXP_MERGEDRES
-      int trips = 0;
-      if (tb->block_width > 0) {
-        for (int w = 0; w < DEXR_MAX_LANES / 4; ++w) {
-          int n = 0;
-          for (int k = 0; k < tb->n_res; ++k) {
-            const uint32_t msk = tb->link_anc_mask[tb->res_task[k]] |
-                                 (tb->res_origin[k] >= 0 ? tb->link_anc_mask[tb->res_origin[k]] : 0u);
-            const int win = msk ? (__ffs(msk) - 1) / tb->block_width : 0;
-            if (win == w) st.win_res[w][n++] = k;
+      {
+        const int gr = tb->block_width > 0 ? tb->block_width : 4;  // lanes per slot
+        const int nslot = DEXR_MAX_LANES / 4;
+        const bool merge = !(tb->block_width == 0 && tb->has_mimic);  // mimic fold: keep one residual per pass
+        for (int r = 0; r < DEXR_MAX_RES; ++r)
+          for (int sl = 0; sl < nslot; ++sl) st.pass_res[r][sl] = -1;
+        int np = 0;
+        for (int k = 0; k < tb->n_res; ++k) {
+          const uint32_t msk = tb->link_anc_mask[tb->res_task[k]] |
+                               (tb->res_origin[k] >= 0 ? tb->link_anc_mask[tb->res_origin[k]] : 0u);
+          uint32_t sm = 0u;  // slots this residual touches; one that touches no joint rides in slot 0 (it still counts
+          for (int sl = 0; sl < nslot && sl * gr < 32; ++sl)  // for the residual maximum)
+            if ((msk >> (sl * gr)) & ((1u << gr) - 1u)) sm |= 1u << sl;
+          if (!sm) sm = 1u;
+          if (!merge) sm = (1u << nslot) - 1u;
+          int r = 0;
+          for (;; ++r) {  // first pass whose slots are all free (pass k at the latest: at most k residuals came before)
+            bool free_pass = true;
+            for (int sl = 0; sl < nslot; ++sl)
+              if (((sm >> sl) & 1u) && st.pass_res[r][sl] >= 0) free_pass = false;
+            if (free_pass) break;
           }
-          trips = n > trips ? n : trips;
-          for (int k = n; k < DEXR_MAX_RES; ++k) st.win_res[w][k] = -1;
+          for (int sl = 0; sl < nslot; ++sl)
+            if ((sm >> sl) & 1u) st.pass_res[r][sl] = k;
+          np = r + 1 > np ? r + 1 : np;
         }
+        st.n_pass = np;
       }
-      st.win_trips = trips;
 #endif
     }
     for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
@@ -576,20 +593,20 @@ struct Solver {
       const float4* lpc = lp(cur);
       float rmax = 0.f;
 #ifdef DEXR_EXP_MERGEDRES
-      constexpr bool merged = BW > 0;
+      constexpr bool merged = !AR;
 #else
       constexpr bool merged = false;
 #endif
       int trips = m;
 #ifdef DEXR_EXP_MERGEDRES
-      if constexpr (merged) trips = ST().win_trips;
+      if constexpr (merged) trips = ST().n_pass;
 #endif
       for (int kk = 0; kk < trips; ++kk) {
         int k = kk;
-        bool on = true;  // merged mode: false on the lanes of a window whose residual list is exhausted
+        bool on = true;  // merged mode: false on the lanes of a slot that has no residual in this pass
 #ifdef DEXR_EXP_MERGEDRES
         if constexpr (merged) {
-          const int kw = ST().win_res[l / (BW > 0 ? BW : 1)][kk];
+          const int kw = ST().pass_res[kk][l / (BW > 0 ? BW : 4)];
           on = kw >= 0;
           k = on ? kw : 0;
         }

@@ -185,27 +185,50 @@ def test_block_width_detection():
         assert build_product(key).optimizer.build_table().block_width == bw, key
 
 
-def test_block_mode_residuals_partition_over_lane_windows():
-    """What the merged residual pass (csrc/dexr_kernels.cuh, DEXR_EXP_MERGEDRES / SharedTable::win_res) relies on: in a
-    block-mode table every residual touches joints of exactly one window of `block_width` lanes, so the per-window lists
-    -- window = lowest touched joint // block_width, window 0 for a residual that touches none -- hold every residual once."""
-    seen = 0
+def _pass_schedule(t):
+    """Mirror of the greedy pass scheduler in load_shared_table (csrc/dexr_kernels.cuh, DEXR_EXP_MERGEDRES)."""
+    gr, nslot = (t.block_width if t.block_width > 0 else 4), 8
+    merge = not (t.block_width == 0 and t.has_mimic)
+    passes, touched = [], []
+    for k in range(t.n_res):
+        m = t.link_anc_mask[t.res_task[k]] | (t.link_anc_mask[t.res_origin[k]] if t.res_origin[k] >= 0 else 0)
+        sm = sum(1 << sl for sl in range(nslot) if sl * gr < 32 and (m >> (sl * gr)) & ((1 << gr) - 1)) or 1
+        if not merge:
+            sm = (1 << nslot) - 1
+        touched.append(sm)
+        r = 0
+        while True:
+            if r == len(passes):
+                passes.append([-1] * nslot)
+            if all(passes[r][sl] < 0 for sl in range(nslot) if (sm >> sl) & 1):
+                break
+            r += 1
+        for sl in range(nslot):
+            if (sm >> sl) & 1:
+                passes[r][sl] = k
+    return passes, touched
+
+
+def test_merged_residual_passes_are_a_valid_schedule():
+    """What the merged residual pass (DEXR_EXP_MERGEDRES, SharedTable::pass_res) relies on, for every shipped configuration:
+    each residual sits in exactly one pass and there owns every lane slot it touches (so all lanes that hold a non-zero
+    Jacobian column for it work on it together, and the columns a lane reads belong to its own residual)."""
+    counts = {}
     for key in sorted(configs()):
         t = build_product(key).optimizer.build_table()
-        if t.block_width == 0:
-            continue
-        seen += 1
-        bw, lists = t.block_width, {}
+        passes, touched = _pass_schedule(t)
+        assert len(passes) <= t.n_res
         for k in range(t.n_res):
-            m = t.link_anc_mask[t.res_task[k]] | (t.link_anc_mask[t.res_origin[k]] if t.res_origin[k] >= 0 else 0)
-            lo, hi = ((m & -m).bit_length() - 1, m.bit_length() - 1) if m else (0, 0)
-            assert lo // bw == hi // bw, (key, k)
-            lists.setdefault(lo // bw, []).append(k)
-        assert sorted(k for v in lists.values() for k in v) == list(range(t.n_res))
-        assert max(lists) < t.dof // bw
-        if "allegro" in key or "leap" in key:  # one fingertip vector per finger: a single pass instead of four
-            assert max(len(v) for v in lists.values()) == 1 and t.n_res == 4
-    assert seen >= 4
+            where = [(r, sl) for r, row in enumerate(passes) for sl, v in enumerate(row) if v == k]
+            assert len({r for r, _ in where}) == 1, (key, k)
+            assert sum(1 << sl for _, sl in where) == touched[k], (key, k)
+        if t.block_width > 0:  # block mode: a residual touches exactly one window
+            assert all(bin(sm).count("1") == 1 for sm in touched), key
+        counts[key] = len(passes)
+    assert counts["teleop/allegro_hand_right"] == 1 and counts["teleop/leap_hand_left"] == 1     # 4 fingertip vectors, 4 fingers
+    assert counts["teleop/leap_hand_right_dexpilot"] == 4 and counts["teleop/allegro_hand_right_dexpilot"] == 4  # 3 rounds of pairs + wrist
+    assert counts["teleop/ability_hand_right"] == 5       # mimic joints: no merging
+    assert counts["offline/shadow_hand_right"] == 10      # every residual touches the free-flying base
 
 
 def test_library_rejects_inconsistent_block_width():
