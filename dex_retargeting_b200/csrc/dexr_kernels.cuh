@@ -113,6 +113,7 @@ __device__ __forceinline__ float huber_val(float d, float beta, float inv_beta) 
   return d < beta ? 0.5f * d * d * inv_beta : d - 0.5f * beta;
 }
 
+#ifndef DEXR_HOST_EMULATION  // tests/emu compiles this header for the host: no PTX there (the kernels stay in dexr.cu)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -146,6 +147,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+#endif  // DEXR_HOST_EMULATION
 
 // Problem dimensions: passed as kernel arguments (constant bank) so that every loop bound and branch that
 // depends on them is provably warp-uniform for the compiler (no divergence scaffolding around shuffles).

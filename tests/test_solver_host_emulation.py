@@ -1,0 +1,127 @@
+"""The CUDA solver SOURCE executed on the host (no GPU): tests/emu compiles dex_retargeting_b200/csrc/dexr_kernels.cuh with
+g++ through a warp shim -- 32 cooperatively scheduled fibers, the warp collectives as rendezvous points, shared memory as a
+NaN-poisoned buffer -- and runs Solver<G, BW>::solve exactly as dexr_frames_kernel does (one frame per group of G lanes).
+What this checks: the logic of every solver instantiation (block, dense 16 / 32 lanes, arrow, mimic fold, DexPilot state),
+the warp-convergence of every collective, the shared-memory ordering (lanes run one after another between collectives, so a
+missing __syncwarp reads stale or NaN data here) and the compile-time experiment switches, all against the float64 oracle.
+What it cannot check: GPU arithmetic in the last bits, the TMA ring / kernels of dexr.cu, performance (the -m gpu tests do)."""
+import numpy as np
+import pytest
+
+import emu_host
+from helpers import build_oracle, build_product, keypoint_trajectory, synth_problems
+
+TOL = 1e-4  # rad / m, BASELINE.json's joint-space tolerance
+
+CASES = [  # key, use_arrow, frames
+    ("teleop/allegro_hand_right", True, 5),          # Solver<16, 4>: block-diagonal, two frames per warp, odd count
+    ("teleop/leap_hand_right_dexpilot", True, 5),    # Solver<16, 0>: dense, DexPilot weights / projected targets
+    ("teleop/ability_hand_right", True, 4),          # Solver<16, 0>: mimic fold
+    ("teleop/shadow_hand_right", True, 3),           # Solver<32, -1>: arrow, trunk of 2 wrist joints
+    ("teleop/shadow_hand_right", False, 3),          # Solver<32, 0>: the same problems through the dense factorisation
+    ("offline/shadow_hand_right", True, 2),          # Solver<32, -1>: position loss, free-flying base (trunk of 8)
+    ("teleop/schunk_svh_hand_right", True, 2),       # Solver<32, 0>: 20 lanes, 11 mimic joints
+]
+VARIANTS = [("DEXR_EXP_SMALLCODE",), ("DEXR_EXP_MERGEDRES",), ("DEXR_EXP_PDFALLBACK",),
+            ("DEXR_EXP_SMALLCODE", "DEXR_EXP_MERGEDRES", "DEXR_EXP_PDFALLBACK")]
+_cache = {}
+
+
+def problems(key, n):
+    o = build_oracle(key)
+    refs, fixed, x0, _ = synth_problems(o, n, np.random.RandomState(3), init_noise=0.05, target_noise=0.01)
+    return o, refs, fixed, x0
+
+
+def oracle_solutions(key, n):
+    from oracle.solvers import solve_converged
+
+    if (key, n) not in _cache:
+        o, refs, fixed, x0 = problems(key, n)
+        X = []
+        for i in range(n):
+            if o.type == "dexpilot":
+                o.projected[:] = False
+            xb, kkt, _ = solve_converged(o, refs[i], fixed[i], x0[i], update_state=False)
+            assert kkt < 1e-6
+            X.append(xb)
+        _cache[key, n] = np.array(X)
+    return _cache[key, n]
+
+
+def emulate(key, n, use_arrow, defines=()):
+    o, refs, fixed, x0 = problems(key, n)
+    opt = build_product(key).optimizer
+    proj = np.zeros((n, len(o.projected)), np.uint8) if o.type == "dexpilot" else None
+    q, status, cost = emu_host.solve_frames(opt, x0, ref_value=refs, fixed_qpos=fixed if fixed.size else None, projected=proj,
+                                           defines=defines, use_arrow=use_arrow)
+    return o, refs, fixed, x0, q, status, cost, proj
+
+
+@pytest.mark.parametrize("key,use_arrow,n", CASES)
+def test_solver_source_matches_oracle(key, use_arrow, n):
+    o, refs, fixed, x0, q, status, cost, proj = emulate(key, n, use_arrow)
+    assert np.all((status >> 24) == 0), "flagged frames"
+    XB = oracle_solutions(key, n)
+    dq = np.abs(q - XB).max(1)
+    assert dq.max() < TOL, dq
+    for i in range(n):  # the reported cost is the consistent objective at the returned point
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        obj = o.make_objective(refs[i], fixed[i], x0[i], update_state=(o.type == "dexpilot"))
+        assert cost[i] == pytest.approx(obj.consistent(q[i].astype(np.float64)), rel=2e-4, abs=1e-8)
+        if o.type == "dexpilot":
+            np.testing.assert_array_equal(proj[i], o.projected.astype(np.uint8))
+
+
+@pytest.mark.parametrize("defines", VARIANTS, ids=lambda d: "+".join(x.replace("DEXR_EXP_", "").lower() for x in d))
+@pytest.mark.parametrize("key,use_arrow,n", CASES)
+def test_experiment_switches(key, use_arrow, n, defines):
+    """Every compile-time experiment (csrc/dexr_kernels.cuh "Experiment switches") solves the same problems: the rolled
+    loops and the merged residual passes reproduce the default build exactly (same arithmetic, minus terms that are
+    exact zeros; where merging reorders the residuals of a lane -- dense DexPilot -- the sums round differently); the PD
+    fallback takes another iteration path and must land on the oracle's minimiser."""
+    _, _, _, _, q0, s0, c0, p0 = emulate(key, n, use_arrow)
+    o, refs, fixed, x0, q, status, cost, proj = emulate(key, n, use_arrow, defines)
+    assert np.all((status >> 24) == 0)
+    reordered = "DEXR_EXP_MERGEDRES" in defines and "dexpilot" in key and use_arrow  # merged passes visit the residuals in
+    if "DEXR_EXP_PDFALLBACK" not in defines and not reordered:             # another order: same sums, other rounding
+        np.testing.assert_array_equal(q, q0)
+        np.testing.assert_array_equal(status, s0)
+    elif "DEXR_EXP_PDFALLBACK" not in defines:
+        assert np.abs(q - q0).max() < 1e-5 and np.abs(q - oracle_solutions(key, n)).max() < TOL
+    else:
+        assert np.abs(q - oracle_solutions(key, n)).max() < TOL
+        assert (status & 0xffff).sum() <= (s0 & 0xffff).sum() + 1  # never slower in iterations on these problems
+    if proj is not None:
+        np.testing.assert_array_equal(proj, p0)
+
+
+def test_keypoint_gather_and_clip_on_recorded_frames():
+    """In-kernel gather from the 21 keypoints (prepare_targets) = the caller-side gather, on recorded human frames with the
+    warm start clipped to the joint limits (SeqRetargeting.retarget's prelude)."""
+    key = "teleop/allegro_hand_right"
+    seq, o = build_product(key), build_oracle(key)
+    kp = keypoint_trajectory()[::40][:4].astype(np.float32)
+    refs = np.stack([o.ref_from_keypoints(k) for k in kp]).astype(np.float32)
+    x0 = np.tile(seq.joint_limits.mean(1).astype(np.float32), (len(kp), 1))
+    x0[1] = seq.joint_limits[:, 1] + 0.2  # outside the limits: clipped before the solve
+    qa, sa, _ = emu_host.solve_frames(seq.optimizer, x0, keypoints=kp, clip_init=True)
+    qb, sb, _ = emu_host.solve_frames(seq.optimizer, x0, ref_value=refs, clip_init=True)
+    np.testing.assert_array_equal(qa, qb)
+    np.testing.assert_array_equal(sa, sb)
+    assert np.all(qa <= seq.joint_limits[:, 1] + 1e-3 + 1e-6) and np.all(qa >= seq.joint_limits[:, 0] - 1e-3 - 1e-6)
+
+
+def test_non_finite_input_is_flagged_and_isolated():
+    """A NaN keypoint flags its frame (status bit 25) and returns the warm start; the other frame of the warp is unaffected."""
+    key = "teleop/allegro_hand_right"
+    o, refs, fixed, x0 = problems(key, 2)
+    opt = build_product(key).optimizer
+    q_ok, s_ok, _ = emu_host.solve_frames(opt, x0, ref_value=refs)
+    bad = refs.copy()
+    bad[0, 1, 2] = np.nan
+    q, s, _ = emu_host.solve_frames(opt, x0, ref_value=bad)
+    assert (s[0] >> 25) & 1 and not (s[1] >> 24)
+    np.testing.assert_array_equal(q[0], x0[0])
+    np.testing.assert_array_equal(q[1], q_ok[1])
