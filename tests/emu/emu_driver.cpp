@@ -165,4 +165,97 @@ extern "C" int emu_solve_frames(const dexr_table_t* tb, const dexr_params_t* prm
   return run_all<32, 0>(err, errlen);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Streams.  The per-stream recurrence of dexr_sequences_kernel (dexr.cu) restated around the same Solver::solve: warm start
+// carried in the lane's register (in.last == nullptr), clip, solve, unfiltered solution = next warm start, low-pass filter
+// on the full joint vector, DexPilot flags read-modify-written in place.  (The kernel stages each frame's keypoints in
+// shared memory first; here solve() reads them where they are.)
+namespace {
+struct SeqJob {
+  dexr_sequences_t io;
+  long long S, base;
+  int T;
+} sjob;
+
+template <int G, int BW>
+void seq_lane_body(int lane) {
+  const Job& j = job;
+  const SeqJob& q = sjob;
+  const int gid = lane / G;
+  Solver<G, BW> sv;
+  sv.init(j.tb, j.dm, (uint32_t)(j.scratch_off + gid * Scratch<G>::kFloats * 4), j.prm, lane);
+  const int l = sv.l;
+  const bool use_filter = j.prm.lp_alpha >= 0.f && j.prm.lp_alpha <= 1.f;
+  const long long s = q.base + gid;
+  const bool active = s < q.S;
+  const long long sc = active ? s : q.S - 1;
+  float last = 0.f, fy = 0.f;
+  int finit = 0;
+  if (active && sv.var >= 0) last = q.io.last_qpos[sc * j.dm.n_var + sv.var];
+  if (active && use_filter && l < j.dm.dof) fy = q.io.filter_state[sc * j.dm.dof + l];
+  if (active && use_filter) finit = q.io.filter_init[sc];
+  for (int t = 0; t < q.T; ++t) {
+    FrameInputs in;
+    in.kp = q.io.keypoints + (sc * q.T + t) * 3 * DEXR_NUM_KEYPOINTS;
+    in.ref = nullptr;
+    in.fixed = j.dm.n_fixed > 0 ? q.io.fixed_qpos + (sc * q.T + t) * j.dm.n_fixed : nullptr;
+    in.last = nullptr;
+    in.projected = q.io.projected ? q.io.projected + sc * j.dm.len_proj : nullptr;
+    sv.x = last;
+    const int status = sv.solve(in, active);
+    last = sv.x;
+    float out = sv.q;
+    if (use_filter) {
+      fy = finit ? fmaf(j.prm.lp_alpha, out - fy, fy) : out;
+      finit = 1;
+      out = fy;
+    }
+    if (active) {
+      if (l < j.dm.dof) q.io.robot_qpos_out[(sc * q.T + t) * j.dm.dof + l] = out;
+      if (l == 0 && q.io.status_out) q.io.status_out[sc * q.T + t] = status;
+    }
+    __syncwarp();
+  }
+  if (active) {
+    if (sv.var >= 0) q.io.last_qpos[sc * j.dm.n_var + sv.var] = last;
+    if (use_filter && l < j.dm.dof) q.io.filter_state[sc * j.dm.dof + l] = fy;
+    if (use_filter && l == 0) q.io.filter_init[sc] = (uint8_t)finit;
+  }
+}
+
+template <int G, int BW>
+int run_streams(char* err, int errlen) {
+  constexpr int GPW = 32 / G;
+  job.scratch_off = ((int)sizeof(SharedTable) + 15) / 16 * 16;
+  const int scratch_bytes = GPW * Scratch<G>::kFloats * 4;
+  threadIdx.x = 0; blockDim.x = 1;
+  load_shared_table(*reinterpret_cast<SharedTable*>(dsmem), job.tb);
+  for (sjob.base = 0; sjob.base < sjob.S; sjob.base += GPW) {
+    uint32_t* sc = reinterpret_cast<uint32_t*>(dsmem + job.scratch_off);
+    for (int i = 0; i < scratch_bytes / 4; ++i) sc[i] = 0x7fc00000u;
+    if (emu::run_warp(&seq_lane_body<G, BW>) != 0) {
+      snprintf(err, errlen, "stream %lld: %s", sjob.base, emu::errmsg);
+      return -1;
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int emu_solve_sequences(const dexr_table_t* tb, const dexr_params_t* prm, int use_arrow, const dexr_sequences_t* io,
+                                   long long S, long long T, char* err, int errlen) {
+  job = Job{};
+  job.tb = tb; job.prm = *prm;
+  job.prm.clip_init = 1;  // launch_sequences: SeqRetargeting.retarget always clips the warm start
+  Dims& d = job.dm;
+  d.dof = tb->dof; d.n_var = tb->n_var; d.n_fixed = tb->n_fixed; d.n_links = tb->n_links; d.n_res = tb->n_res; d.loss = tb->loss;
+  d.n_rounds = tb->n_rounds; d.has_mimic = tb->has_mimic; d.num_fingers = tb->num_fingers; d.len_proj = tb->len_proj;
+  d.len_s1 = tb->len_s1; d.block_width = tb->block_width; d.trunk = tb->arrow > 0 ? tb->arrow - 1 : 0;
+  sjob.io = *io; sjob.S = S; sjob.T = (int)T;
+  if (S <= 0 || T <= 0) return 0;
+  if (tb->dof <= 16) return tb->block_width == 4 ? run_streams<16, 4>(err, errlen) : run_streams<16, 0>(err, errlen);
+  if (tb->arrow > 0 && use_arrow) return run_streams<32, -1>(err, errlen);
+  return run_streams<32, 0>(err, errlen);
+}
+
 extern "C" long long emu_rounds() { return emu::n_rounds_total; }

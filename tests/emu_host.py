@@ -62,3 +62,34 @@ def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None
     if rc != 0:
         raise RuntimeError(f"host emulation failed ({rc}): {err.value.decode()}")
     return out, status, cost
+
+
+def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True):
+    """Emulated dexr_solve_sequences for a SeqRetargeting of the host mirror: keypoints [S,T,21,3] -> filtered robot qpos
+    [S,T,dof]; `state` = dict(last_qpos, filter_state, filter_init, projected) carried between calls (created if None)."""
+    from dex_retargeting_b200 import _native as N
+
+    lib = load(tuple(defines))
+    opt = seq.optimizer
+    table, prm = opt.build_table(), opt.params(clip_init=True, lp_alpha=seq.low_pass_alpha)
+    kp = np.ascontiguousarray(keypoints, dtype=np.float32)
+    S, T = kp.shape[:2]
+    assert table.n_fixed == 0, "streams with fixed joints: not wired in the emulation helper"
+    if state is None:  # SeqRetargeting.make_stream_state: mid-range warm start, filter not initialised, no projection
+        state = dict(last_qpos=np.tile(seq.joint_limits.mean(1).astype(np.float32), (S, 1)),
+                     filter_state=np.zeros((S, table.dof), np.float32), filter_init=np.zeros(S, np.uint8),
+                     projected=np.zeros((S, table.len_proj), np.uint8) if opt.retargeting_type == "DEXPILOT" else None)
+    out = np.full((S, T, table.dof), np.nan, np.float32)
+    status = np.zeros((S, T), np.int32)
+    io = N.DexrSequences()
+    io.keypoints, io.last_qpos = kp.ctypes.data, state["last_qpos"].ctypes.data
+    io.filter_state, io.filter_init = state["filter_state"].ctypes.data, state["filter_init"].ctypes.data
+    io.projected = state["projected"].ctypes.data if state["projected"] is not None else None
+    io.robot_qpos_out, io.status_out = out.ctypes.data, status.ctypes.data
+    err = C.create_string_buffer(600)
+    lib.emu_solve_sequences.restype = C.c_int
+    rc = lib.emu_solve_sequences(C.byref(table), C.byref(prm), C.c_int(int(use_arrow)), C.byref(io), C.c_longlong(S),
+                                 C.c_longlong(T), err, C.c_int(600))
+    if rc != 0:
+        raise RuntimeError(f"host emulation failed ({rc}): {err.value.decode()}")
+    return out, status, state

@@ -125,3 +125,52 @@ def test_non_finite_input_is_flagged_and_isolated():
     assert (s[0] >> 25) & 1 and not (s[1] >> 24)
     np.testing.assert_array_equal(q[0], x0[0])
     np.testing.assert_array_equal(q[1], q_ok[1])
+
+
+@pytest.mark.parametrize("key,vs_oracle", [("teleop/allegro_hand_right", True), ("teleop/leap_hand_right_dexpilot", False),
+                                           ("teleop/schunk_svh_hand_right", True)])
+def test_streams_recurrence(key, vs_oracle):
+    """The stream recurrence around the same solve() (warm start carried in the lane's register, clip, unfiltered solution =
+    next warm start, low-pass filter, DexPilot flags in place; restated from dexr_sequences_kernel in tests/emu) equals the
+    frame-by-frame twin through the frames entry bit for bit, and the oracle's SeqRetargeting where basins are unambiguous."""
+    from oracle.solvers import OracleSeqRetargeting
+
+    seq = build_product(key)
+    opt = seq.optimizer
+    S, T = 3, 8
+    kp = keypoint_trajectory()
+    kps = np.stack([kp[s:s + 2 * T:2] for s in (0, 150, 400)]).astype(np.float32)
+    got, status, state = emu_host.solve_sequences(seq, kps)
+    assert np.all((status >> 24) == 0)
+    # frame-by-frame twin
+    last = np.tile(seq.joint_limits.mean(1).astype(np.float32), (S, 1))
+    proj = np.zeros((S, opt._objective_spec().len_proj), np.uint8) if opt.retargeting_type == "DEXPILOT" else None
+    y = None
+    for t in range(T):
+        q, _, _ = emu_host.solve_frames(opt, last, keypoints=kps[:, t], projected=proj, clip_init=True)
+        last = q
+        full = np.zeros((S, opt.robot.dof), np.float32)
+        full[:, opt.idx_pin2target] = q
+        if opt.adaptor is not None:
+            full = np.stack([opt.adaptor.forward_qpos(r.astype(np.float64)) for r in full]).astype(np.float32)
+        y = full if y is None else y + np.float32(seq.low_pass_alpha) * (full - y)
+        np.testing.assert_allclose(got[:, t], y, atol=2e-6, err_msg=f"{key} step {t}")
+    np.testing.assert_array_equal(state["last_qpos"], last)
+    if proj is not None:
+        np.testing.assert_array_equal(state["projected"], proj)
+    if vs_oracle:
+        want = np.zeros((S, T, opt.robot.dof))
+        for s in range(S):
+            oseq = OracleSeqRetargeting(build_oracle(key), mode="converged")
+            for t in range(T):
+                want[s, t] = oseq.retarget(oseq.opt.ref_from_keypoints(kps[s, t]))
+        assert np.abs(got - want).max() < TOL
+    # the state is complete: two calls = one call
+    out1, _, st = emu_host.solve_sequences(seq, kps[:, :3])
+    out2, _, st = emu_host.solve_sequences(seq, kps[:, 3:], state=st)
+    np.testing.assert_array_equal(np.concatenate([out1, out2], axis=1), got)
+    # and with every experiment switch on: same streams within the solver tolerance
+    exp, st_e, _ = emu_host.solve_sequences(seq, kps, defines=VARIANTS[-1])
+    assert np.all((st_e >> 24) == 0)
+    if vs_oracle:
+        assert np.abs(exp - want).max() < TOL
