@@ -36,8 +36,9 @@ def load(defines: tuple = ()):
 
 
 def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None, projected=None, defines=(), use_arrow=True,
-                 clip_init=False):
-    """Emulated dexr_solve_frames for an Optimizer of the host mirror.  Returns (qpos [B,n], status [B], cost [B])."""
+                 clip_init=False, want_robot_qpos=False):
+    """Emulated dexr_solve_frames for an Optimizer of the host mirror.  Returns (qpos [B,n], status [B], cost [B])
+    (+ the full joint vector [B,dof] with want_robot_qpos)."""
     from dex_retargeting_b200 import _native as N
 
     lib = load(tuple(defines))
@@ -57,11 +58,12 @@ def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None
     def ptr(a):
         return None if a is None else a.ctypes.data_as(C.c_void_p)
 
+    full = np.zeros((B, table.dof), np.float32) if want_robot_qpos else None
     rc = lib.emu_solve_frames(C.byref(table), C.byref(prm), C.c_int(int(use_arrow)), ptr(kp), ptr(ref), ptr(last), ptr(fixed),
-                              ptr(projected), C.c_longlong(B), ptr(out), None, ptr(status), ptr(cost), err, C.c_int(600))
+                              ptr(projected), C.c_longlong(B), ptr(out), ptr(full), ptr(status), ptr(cost), err, C.c_int(600))
     if rc != 0:
         raise RuntimeError(f"host emulation failed ({rc}): {err.value.decode()}")
-    return out, status, cost
+    return (out, status, cost, full) if want_robot_qpos else (out, status, cost)
 
 
 def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True):

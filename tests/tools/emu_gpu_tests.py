@@ -1,67 +1,160 @@
 #!/usr/bin/env python
-"""Run the bodies of the frames-mode GPU parity tests (tests/test_gpu_parity.py) against the HOST EMULATION of the solver
-source instead of the CUDA library -- for a chosen set of compile-time experiment switches.  A dry run on the CPU of what
-`pytest -m gpu` will check on a B200 (minus GPU arithmetic in the last bits, minus the kernels of dexr.cu).
+"""Dry run of the GPU parity suite on the CPU: the test functions of tests/test_gpu_{parity,golden,arrow}.py are called
+unchanged while the two device entry points of the host mirror (Optimizer.retarget_batch, SeqRetargeting.retarget_sequences)
+are served by the HOST EMULATION of the solver source (tests/emu) -- for a chosen set of compile-time experiment switches.
+Inside the test modules `torch` is a proxy that maps every device to the CPU.  Not covered: the pinned-host entry, multi-GPU,
+anything that is specific to the kernels of dexr.cu (tile ring, alignment paths), GPU arithmetic in the last bits.
 
-  python tests/tools/emu_gpu_tests.py                         # default build of the solver
-  python tests/tools/emu_gpu_tests.py DEXR_EXP_PDFALLBACK DEXR_EXP_MERGEDRES
+  python tests/tools/emu_gpu_tests.py                                   # default build of the solver
+  python tests/tools/emu_gpu_tests.py DEXR_EXP_PDFALLBACK DEXR_EXP_MERGEDRES [-k substring]
 """
+import itertools
+import os
 import sys
+import tempfile
 import time
 import traceback
 from pathlib import Path
 
 import numpy as np
+import torch as real_torch
 
 ROOT = Path(__file__).resolve().parents[2]
 for p in (ROOT, ROOT / "tests"):
     sys.path.insert(0, str(p))
 import emu_host  # noqa: E402
-import test_gpu_parity as T  # noqa: E402
+from dex_retargeting_b200.optimizer import Optimizer  # noqa: E402
+from dex_retargeting_b200.seq_retarget import SeqRetargeting, StreamState  # noqa: E402
 
-DEFINES = tuple(sys.argv[1:])
+ARGS = sys.argv[1:]
+KEYWORD = ARGS[ARGS.index("-k") + 1] if "-k" in ARGS else None
+DEFINES = tuple(a for a in ARGS if a.startswith("DEXR_EXP_"))
+SKIP = {"test_host_buffer_entry_matches_device_entry": "pinned-host entry (dexr_solve_frames_host)",
+        "test_batch_shapes_alignment_and_determinism": "alignment / tile paths of the CUDA kernel",
+        "test_full_batch_properties": "65 536-frame batch (hours under emulation)",
+        "test_single_frame_api_matches_batch_and_oracle": "single-frame host entry",
+        "test_maximum_size_robot_parity": "uses the host entry",
+        "test_empty_batch_is_a_no_op": "host entry"}
 
 
-def emu_solve(opt, refs=None, fixed=None, x0=None, keypoints=None, clip_init=False, want_proj=False, proj_init=None):
-    B = x0.shape[0]
-    proj = None
-    if opt.retargeting_type == "DEXPILOT":
-        lp = opt._objective_spec().len_proj
-        proj = np.zeros((B, lp), np.uint8) if proj_init is None else np.ascontiguousarray(proj_init, dtype=np.uint8).copy()
-    fx = fixed if (fixed is not None and fixed.shape[1] > 0) else None
-    q, status, cost = emu_host.solve_frames(opt, x0, keypoints=keypoints, ref_value=None if keypoints is not None else refs,
-                                           fixed_qpos=fx, projected=proj, defines=DEFINES, clip_init=clip_init)
-    full = np.zeros((B, opt.robot.dof), np.float32)  # scatter + mimic like the kernel's optional robot_qpos output
-    full[:, opt.idx_pin2target] = q
-    if fx is not None:
-        full[:, opt.idx_pin2fixed] = fx
-    if opt.adaptor is not None:
-        full = np.stack([opt.adaptor.forward_qpos(r.astype(np.float64)) for r in full]).astype(np.float32)
-    res = dict(q=q, status=status, cost=cost, robot_qpos=full)
-    if proj is not None:
-        res["projected"] = proj
-    return res
+class FakeEngine:
+    """Stands in for optimizer._Engine (which creates the device copy of the table): only launch_info is asked for."""
+
+    def __init__(self, opt):
+        t = opt.build_table()
+        self.lanes = 16 if t.dof <= 16 else 32
+
+    def launch_info(self):
+        return dict(grid=1, block=32, smem_bytes=0, frames_per_tile=32 // self.lanes, lanes_per_frame=self.lanes,
+                    consumer_warps=1, kernels_launched=0)
+
+
+class _Cuda:
+    synchronize = staticmethod(lambda *a, **k: None)
+    is_available = staticmethod(lambda: True)
+    device_count = staticmethod(lambda: 1)
+
+
+class TorchProxy:
+    cuda = _Cuda()
+
+    def device(self, *a, **k):
+        return real_torch.device("cpu")
+
+    def __getattr__(self, name):
+        return getattr(real_torch, name)
+
+
+def _np(t):
+    return None if t is None else t.detach().numpy()
+
+
+def use_arrow():
+    return os.environ.get("DEXR_ARROW", "1") != "0"
+
+
+def retarget_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None, out=None,
+                   robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None):
+    B = last_qpos.shape[0]
+    if B == 0:
+        return real_torch.empty((0, self.opt_dof)) if out is None else out
+    q, status, cost, full = emu_host.solve_frames(self, _np(last_qpos), keypoints=_np(keypoints), ref_value=_np(ref_value),
+                                                 fixed_qpos=_np(fixed_qpos), projected=_np(projected), defines=DEFINES,
+                                                 use_arrow=use_arrow(), clip_init=clip_init, want_robot_qpos=True)
+    for dst, src in ((status_out, status), (cost_out, cost), (robot_qpos_out, full)):
+        if dst is not None:
+            dst.copy_(real_torch.from_numpy(src))
+    if out is not None:
+        out.copy_(real_torch.from_numpy(q))
+        return out
+    return real_torch.from_numpy(q)
+
+
+def make_stream_state(self, num_streams):
+    opt = self.optimizer
+    lp = opt._objective_spec().len_proj
+    return StreamState(last_qpos=real_torch.from_numpy(np.tile(self.joint_limits.mean(1).astype(np.float32), (num_streams, 1))),
+                       filter_state=real_torch.zeros((num_streams, opt.robot.dof)), filter_init=real_torch.zeros(num_streams, dtype=real_torch.uint8),
+                       projected=real_torch.zeros((num_streams, lp), dtype=real_torch.uint8) if lp else None)
+
+
+def retarget_sequences(self, keypoints, state=None, fixed_qpos=None, out=None, status_out=None, stream=None):
+    S = keypoints.shape[0]
+    state = state if state is not None else self.make_stream_state(S)
+    st = dict(last_qpos=_np(state.last_qpos), filter_state=_np(state.filter_state), filter_init=_np(state.filter_init),
+              projected=_np(state.projected))
+    got, status, _ = emu_host.solve_sequences(self, _np(keypoints), state=st, defines=DEFINES, use_arrow=use_arrow())
+    if status_out is not None:
+        status_out.copy_(real_torch.from_numpy(status))
+    if out is not None:
+        out.copy_(real_torch.from_numpy(got))
+        return out, state
+    return real_torch.from_numpy(got), state
+
+
+def expand(fn):
+    marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+    axes = []
+    for m in marks:
+        names = [n.strip() for n in m.args[0].split(",")]
+        axes.append([dict(zip(names, v if len(names) > 1 else (v,))) for v in m.args[1]])
+    for combo in itertools.product(*axes) if axes else [()]:
+        kw = {}
+        for d in combo:
+            kw.update(d)
+        yield kw
 
 
 def main():
-    T.gpu_solve = emu_solve
-    jobs = [(T.test_synthetic_warm_start_parity, dict(key=k, ov=ov)) for k, ov in T.FAMILIES]
-    jobs += [(T.test_recorded_trajectory_parity, dict(key=k)) for k in
-             ["teleop/allegro_hand_right", "teleop/shadow_hand_right", "teleop/schunk_svh_hand_right", "teleop/leap_hand_right_dexpilot"]]
-    for mark in getattr(T.test_reference_test_protocol, "pytestmark", []):
-        if mark.name == "parametrize":
-            jobs += [(T.test_reference_test_protocol, dict(zip(("key", "kind"), v))) for v in mark.args[1]]
-    jobs += [(T.test_nonfinite_input_does_not_poison_neighbours, {}), (T.test_bounds_are_respected_and_active, {})]
-    failed = 0
-    for fn, kw in jobs:
-        t0 = time.time()
-        try:
-            fn(**kw)
-            print(f"PASS {fn.__name__} {kw} [{time.time() - t0:.1f}s]", flush=True)
-        except Exception:
-            failed += 1
-            print(f"FAIL {fn.__name__} {kw}\n{traceback.format_exc(limit=3)}", flush=True)
-    print(f"{len(jobs) - failed}/{len(jobs)} passed with defines {DEFINES or '(default)'}")
+    Optimizer.retarget_batch = retarget_batch
+    Optimizer.engine = lambda self: FakeEngine(self)
+    SeqRetargeting.make_stream_state = make_stream_state
+    SeqRetargeting.retarget_sequences = retarget_sequences
+    import test_gpu_arrow, test_gpu_golden, test_gpu_parity  # noqa: E401
+
+    failed = ran = 0
+    for mod in (test_gpu_parity, test_gpu_golden, test_gpu_arrow):
+        mod.torch = TorchProxy()
+        for name in [n for n in dir(mod) if n.startswith("test_")]:
+            fn = getattr(mod, name)
+            if name in SKIP:
+                print(f"SKIP {name}: {SKIP[name]}")
+                continue
+            for kw in expand(fn):
+                label = f"{mod.__name__}::{name} {kw if kw else ''}"
+                if KEYWORD and KEYWORD not in label:
+                    continue
+                if "tmp_path" in fn.__code__.co_varnames[:fn.__code__.co_argcount]:
+                    kw = dict(kw, tmp_path=Path(tempfile.mkdtemp()))
+                t0 = time.time()
+                ran += 1
+                try:
+                    fn(**kw)
+                    print(f"PASS {label} [{time.time() - t0:.1f}s]", flush=True)
+                except Exception:
+                    failed += 1
+                    print(f"FAIL {label}\n{traceback.format_exc(limit=4)}", flush=True)
+    print(f"{ran - failed}/{ran} passed with defines {DEFINES or '(default)'}")
     return failed
 
 
