@@ -32,7 +32,9 @@ VARIANTS = {
     "smallcode_fastsincos": ["-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_FASTSINCOS"],
     "pdfallback": ["-DDEXR_EXP_PDFALLBACK"],
     "pdfallback_smallcode": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_SMALLCODE"],
-    "all": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_MERGEDRES"],
+    "fknoise": ["-DDEXR_EXP_FKNOISE"],
+    "pdfallback_fknoise": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_FKNOISE"],
+    "all": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_FKNOISE", "-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_MERGEDRES"],
     "mergedres": ["-DDEXR_EXP_MERGEDRES"],
     "mergedres_smallcode": ["-DDEXR_EXP_MERGEDRES", "-DDEXR_EXP_SMALLCODE"],
 }

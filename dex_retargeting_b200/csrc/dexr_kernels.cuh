@@ -44,6 +44,11 @@
 //                        with the positive semi-definite model, instead of multiplying the damping by 10 and refactorising
 //                        until it dominates (fp32 solver model: Shadow position 7.7 -> 5.3 iterations, 10.0 -> 5.3
 //                        factorisations per frame; neutral on warm-started streams and unreachable targets)
+//   DEXR_EXP_FKNOISE     noise floor of the objective for the acceptance test: kNoise |F| PLUS the fp32 resolution of the link
+//                        positions seen through the loss, 2 ulp x sum_k w_k |p_k|_1 (the Huber slope is at most 1).  With
+//                        link positions of ~0.5 m (free-flying base) F ~ 1e-3 is only resolved to ~2e-8, ten times coarser
+//                        than kNoise |F|: a converging Newton step with a predicted decrease of 7e-9 gets rejected on a
+//                        noise bump, the damping escalates, and the frame stops on a damped step 4e-4 rad from the minimiser
 //   DEXR_EXP_MERGEDRES   a residual only touches the joints above its links; residuals that touch disjoint sets of lane
 //                        slots (block mode: the block_width-lane windows; dense mode: 4-lane chunks) are packed into the
 //                        same pass (greedy, once per CTA: SharedTable::pass_res) and every lane works on the residual of
@@ -315,6 +320,10 @@ struct Solver {
   float x, x0, q, qfix;       // variable value, anchor, full joint value, fixed value
   float R[9], p[3], a[3];     // world placement of this joint frame, world axis (at accepted x)
   float F;                    // objective at x
+#ifdef DEXR_EXP_FKNOISE
+  float Fnz;                  // sum_k w_k |p_k|_1 at x: scale of the fp32 position noise in F
+  mutable float cost_nz;      // the same for the last cost() call
+#endif
   int cur;                    // which link-position buffer holds the accepted positions
 
   __device__ __forceinline__ static const SharedTable& ST() { return *reinterpret_cast<const SharedTable*>(dsmem); }
@@ -424,16 +433,28 @@ struct Solver {
   // 263-274, 524-541, with the regulariser the reference only puts into the gradient).
   __device__ __forceinline__ float cost(int b, float xv) const {
     float v = 0.f;
+#ifdef DEXR_EXP_FKNOISE
+    float nz = 0.f;
+#endif
     const int m = dm.n_res;
     if (l < m) {
       const float4 T = fr()[l];
       const int ti = ST().res_task[l], oi = ST().res_origin[l];
       const float4 pt = lp(b)[ti];
       float rx = pt.x - T.x, ry = pt.y - T.y, rz = pt.z - T.z;
+#ifdef DEXR_EXP_FKNOISE
+      nz = fabsf(pt.x) + fabsf(pt.y) + fabsf(pt.z);
+#endif
       if (oi >= 0) {
         const float4 po = lp(b)[oi];
         rx -= po.x; ry -= po.y; rz -= po.z;
+#ifdef DEXR_EXP_FKNOISE
+        nz += fabsf(po.x) + fabsf(po.y) + fabsf(po.z);
+#endif
       }
+#ifdef DEXR_EXP_FKNOISE
+      nz *= T.w;
+#endif
       const float beta = prm.huber_delta;
       if (dm.loss == DEXR_LOSS_POSITION) {
         v = T.w * (huber_val(fabsf(rx), beta, inv_beta) + huber_val(fabsf(ry), beta, inv_beta) +
@@ -446,6 +467,9 @@ struct Solver {
       const float dx = xv - x0;
       v = fmaf(prm.norm_delta * dx, dx, v);
     }
+#ifdef DEXR_EXP_FKNOISE
+    cost_nz = gsum<G>(nz);
+#endif
     return gsum<G>(v);
   }
 
@@ -540,6 +564,9 @@ struct Solver {
     write_links(R, p, cur);
     __syncwarp();
     F = cost(cur, x);
+#ifdef DEXR_EXP_FKNOISE
+    Fnz = cost_nz;
+#endif
 
     float lam = prm.lambda0;
     int iters = 0, rejects = 0;
@@ -1060,7 +1087,11 @@ struct Solver {
         write_links(Rn, pn, cur ^ 1);
         __syncwarp();
         const float Fn = cost(cur ^ 1, xn);
+#ifdef DEXR_EXP_FKNOISE
+        const float fnoise = fmaf(kNoise, fabsf(F), 1.2e-7f * fmaxf(Fnz, cost_nz));
+#else
         const float fnoise = kNoise * fabsf(F);
+#endif
         const bool ok = !bad && isfinite(Fn) && (Fn <= F || step < prm.tol || pred < fnoise);
         // the damping is relaxed only after a decrease that fp32 can actually resolve; steps accepted on
         // trust (below the noise floor of F) keep it, so the iteration contracts instead of wandering
@@ -1068,6 +1099,9 @@ struct Solver {
         if (!accepted) {
           if (ok) {
             x = xn; q = qn; F = Fn;
+#ifdef DEXR_EXP_FKNOISE
+            Fnz = cost_nz;
+#endif
 #pragma unroll
             for (int i = 0; i < 9; ++i) R[i] = Rn[i];
 #pragma unroll

@@ -22,8 +22,8 @@ CASES = [  # key, use_arrow, frames
     ("offline/shadow_hand_right", True, 2),          # Solver<32, -1>: position loss, free-flying base (trunk of 8)
     ("teleop/schunk_svh_hand_right", True, 2),       # Solver<32, 0>: 20 lanes, 11 mimic joints
 ]
-VARIANTS = [("DEXR_EXP_SMALLCODE",), ("DEXR_EXP_MERGEDRES",), ("DEXR_EXP_PDFALLBACK",),
-            ("DEXR_EXP_SMALLCODE", "DEXR_EXP_MERGEDRES", "DEXR_EXP_PDFALLBACK")]
+VARIANTS = [("DEXR_EXP_SMALLCODE",), ("DEXR_EXP_MERGEDRES",), ("DEXR_EXP_FKNOISE",), ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE"),
+            ("DEXR_EXP_SMALLCODE", "DEXR_EXP_MERGEDRES", "DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE")]
 _cache = {}
 
 
@@ -85,14 +85,15 @@ def test_experiment_switches(key, use_arrow, n, defines):
     o, refs, fixed, x0, q, status, cost, proj = emulate(key, n, use_arrow, defines)
     assert np.all((status >> 24) == 0)
     reordered = "DEXR_EXP_MERGEDRES" in defines and "dexpilot" in key and use_arrow  # merged passes visit the residuals in
-    if "DEXR_EXP_PDFALLBACK" not in defines and not reordered:             # another order: same sums, other rounding
+    path_changing = {"DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE"} & set(defines)  # other acceptance decisions: other iterates
+    if not path_changing and not reordered:                                 # (reordered: same sums, other rounding)
         np.testing.assert_array_equal(q, q0)
         np.testing.assert_array_equal(status, s0)
-    elif "DEXR_EXP_PDFALLBACK" not in defines:
+    elif not path_changing:
         assert np.abs(q - q0).max() < 1e-5 and np.abs(q - oracle_solutions(key, n)).max() < TOL
     else:
         assert np.abs(q - oracle_solutions(key, n)).max() < TOL
-        assert (status & 0xffff).sum() <= (s0 & 0xffff).sum() + 1  # never slower in iterations on these problems
+        assert (status & 0xffff).sum() <= (s0 & 0xffff).sum() + 2  # not slower in iterations on these problems
     if proj is not None:
         np.testing.assert_array_equal(proj, p0)
 
@@ -174,3 +175,25 @@ def test_streams_recurrence(key, vs_oracle):
     assert np.all((st_e >> 24) == 0)
     if vs_oracle:
         assert np.abs(exp - want).max() < TOL
+
+
+def test_position_noise_floor_keeps_newton_steps_near_the_minimiser():
+    """Shadow position on a free-flying base: link positions of ~0.5 m resolve F ~ 1.3e-3 to ~2e-8 only, ten times coarser
+    than kNoise |F|.  With the PD fallback alone, frame 38 of this batch rejects its converging Newton step on a noise bump,
+    escalates the damping and stops on a damped step 4e-4 rad from the minimiser (arrow elimination order); with the
+    position-noise floor (DEXR_EXP_FKNOISE) every frame ends on the oracle's minimiser, in both elimination orders, with the
+    same iteration counts."""
+    from oracle.solvers import solve_converged
+
+    key = "offline/shadow_hand_right"
+    opt, o = build_product(key).optimizer, build_oracle(key)
+    refs, fixed, x0, _ = synth_problems(o, 48, np.random.RandomState(5), init_noise=0.05, target_noise=0.01)
+    sel = [36, 37, 38, 39]
+    XB = np.array([solve_converged(o, refs[i], fixed[i], x0[i], update_state=False)[0] for i in sel])
+    both = ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE")
+    qa, sa, _ = emu_host.solve_frames(opt, x0[sel], ref_value=refs[sel], defines=both, use_arrow=True)
+    qd, sd, _ = emu_host.solve_frames(opt, x0[sel], ref_value=refs[sel], defines=both, use_arrow=False)
+    assert np.abs(qa - XB).max() < 1e-5 and np.abs(qd - XB).max() < 1e-5
+    np.testing.assert_array_equal(sa & 0xffff, sd & 0xffff)
+    q_old, _, _ = emu_host.solve_frames(opt, x0[sel], ref_value=refs[sel], defines=("DEXR_EXP_PDFALLBACK",), use_arrow=True)
+    assert np.abs(q_old - XB).max() > 1e-4  # documents the failure mode the floor removes (drop this line once it is the default)

@@ -30,7 +30,7 @@ PY
 case "${1:-bench}" in
 bench)
   bench_one base DEXR_NOP=1
-  for v in smallcode fastsincos mergedres mergedres_smallcode pdfallback all; do bench_one "$v" "$(lib $v)"; done
+  for v in smallcode fastsincos mergedres mergedres_smallcode fknoise pdfallback pdfallback_fknoise all; do bench_one "$v" "$(lib $v)"; done
   for w in 20 24; do
     bench_one "w$w" DEXR_G16_WARPS=$w
     bench_one "all_w$w" "$(lib all)" DEXR_G16_WARPS=$w
