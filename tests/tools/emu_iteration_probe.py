@@ -17,7 +17,8 @@ import emu_host  # noqa: E402
 from bench_configs import synth  # noqa: E402
 from helpers import build_product  # noqa: E402
 
-VARIANTS = [(), ("DEXR_EXP_PDFALLBACK",), ("DEXR_EXP_MERGEDRES",), ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_MERGEDRES", "DEXR_EXP_SMALLCODE")]
+VARIANTS = [(), ("DEXR_EXP_MERGEDRES",), ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE"),
+            ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE", "DEXR_EXP_MERGEDRES", "DEXR_EXP_SMALLCODE")]
 
 
 def main(key, B, tol=None):
@@ -30,11 +31,14 @@ def main(key, B, tol=None):
     for d in VARIANTS:
         t0 = time.time()
         proj = np.zeros((B, opt._objective_spec().len_proj), np.uint8) if opt.retargeting_type == "DEXPILOT" else None
+        lib = emu_host.load(tuple(d))
+        r0 = lib.emu_rounds()
         q, st, cost = emu_host.solve_frames(opt, x0, keypoints=kp, fixed_qpos=fixed, projected=proj, defines=d)
+        rounds = (lib.emu_rounds() - r0) / B  # warp collectives (shuffles, ballots, __syncwarp) per frame: a latency proxy
         it, rej = st & 0xffff, (st >> 16) & 0xff
         base = q if base is None else base
         print(f"{'+'.join(x.replace('DEXR_EXP_', '').lower() for x in d) or 'default':32s} iterations {it.mean():.3f} (max {it.max()}) "
-              f"extra trial solves {rej.mean():.3f}  flagged {(st >> 24 != 0).sum()}  max |dq| vs default {np.abs(q - base).max():.2e}  "
+              f"extra trial solves {rej.mean():.3f}  collectives/frame {rounds:.0f}  flagged {(st >> 24 != 0).sum()}  max |dq| vs default {np.abs(q - base).max():.2e}  "
               f"[{time.time() - t0:.1f}s]", flush=True)
 
 
