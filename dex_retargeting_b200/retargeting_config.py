@@ -69,7 +69,9 @@ class RetargetingConfig:
     low_pass_alpha: float = 0.1
 
     _TYPE = ["vector", "position", "dexpilot"]
-    _DEFAULT_URDF_DIR = "./"
+    # the kinematics-only URDFs shipped with the package (the reference defaults to "./" and expects the caller to point
+    # it at a dex-urdf checkout, retargeting_config.py:60; set_default_urdf_dir() still does that)
+    _DEFAULT_URDF_DIR = str(Path(__file__).resolve().parent / "assets" / "robots" / "hands")  # = packaged_urdf_dir()
 
     # what each retargeting type needs from the config: required keys, and the shape of target_link_human_indices as a
     # function of the number of targets (None = optional, DexPilot derives it from the finger count)
@@ -110,14 +112,20 @@ class RetargetingConfig:
 
     @classmethod
     def _resolve_robot_file(cls, name: Union[str, Path]) -> Path:
-        """Absolute path of the robot description: as given, else under the default URDF directory, else the flat JSON
-        joint tree of the same stem there (tests/golden/robots)."""
-        base = Path(cls._DEFAULT_URDF_DIR)
+        """Absolute path of the robot description (`.urdf`, or a `.json` joint tree): as given, else under the default
+        URDF directory.  A path that does not exist is an error, as in the reference (retargeting_config.py:93-96)."""
         path = Path(name)
-        for cand in (path if path.is_absolute() else (base / path).absolute(), (base / (path.stem + ".json")).absolute()):
-            if cand.exists():
-                return cand
-        raise ValueError(f"URDF path {path if path.is_absolute() else (base / path).absolute()} does not exist")
+        if not path.is_absolute():
+            path = (Path(cls._DEFAULT_URDF_DIR) / path).absolute()
+        if not path.exists():
+            raise ValueError(f"URDF path {path} does not exist")
+        return path
+
+    @staticmethod
+    def packaged_urdf_dir() -> Path:
+        """Directory of the kinematics-only hand URDFs shipped with the package (same relative paths as dex-urdf's
+        `robots/hands`, which is what the `urdf_path` entries of the YAML files are relative to)."""
+        return Path(__file__).resolve().parent / "assets" / "robots" / "hands"
 
     @classmethod
     def set_default_urdf_dir(cls, urdf_dir: Union[str, Path]):

@@ -175,6 +175,34 @@ class KinematicModel:
                 return cls.from_dict(json.load(f), add_dummy_free_joints)
         return cls.from_urdf(p, add_dummy_free_joints)
 
+    def write_urdf(self, path) -> None:
+        """Kinematics-only URDF of this joint tree (links without geometry or inertia; joints with origin, axis, limit,
+        mimic), written with 17 significant digits so that reading it back reproduces every float exactly.  This is what
+        ships under `dex_retargeting_b200/assets/robots/hands/` -- the retargeting path needs nothing else from a URDF."""
+        num = lambda v: " ".join(repr(float(x)) for x in v)  # noqa: E731
+        root = ET.Element("robot", name=self.name)
+        for link in self.urdf_link_names:
+            ET.SubElement(root, "link", name=link)
+        for j in self.joints:
+            e = ET.SubElement(root, "joint", name=j.name, type=j.type)
+            ET.SubElement(e, "parent", link=j.parent)
+            ET.SubElement(e, "child", link=j.child)
+            ET.SubElement(e, "origin", xyz=num(j.xyz), rpy=num(j.rpy))
+            if j.type != "fixed":
+                ET.SubElement(e, "axis", xyz=num(j.axis))
+            if j.lower is not None or j.upper is not None:
+                lim = {}
+                if j.lower is not None:
+                    lim["lower"] = repr(float(j.lower))
+                if j.upper is not None:
+                    lim["upper"] = repr(float(j.upper))
+                ET.SubElement(e, "limit", effort="1", velocity="1", **lim)
+            if j.mimic is not None:
+                ET.SubElement(e, "mimic", joint=j.mimic[0], multiplier=repr(float(j.mimic[1])), offset=repr(float(j.mimic[2])))
+        ET.indent(root, space=" ")
+        Path(str(path)).parent.mkdir(parents=True, exist_ok=True)
+        ET.ElementTree(root).write(str(path), encoding="unicode", xml_declaration=True)
+
     def to_dict(self) -> dict:
         """URDF-level description (before any dummy joints were added by this object's caller)."""
         return dict(name=self.name, links=list(self.urdf_link_names), joints=[j.to_dict() for j in self.joints])

@@ -172,9 +172,14 @@ def test_euler_extraction_roundtrip():
         np.testing.assert_allclose(_intrinsic_xyz_from_matrix(Rx @ Ry @ Rz), [a, b, c], atol=1e-12)
 
 
-def test_packaged_default_configs_load_with_fixture_robots():
-    """The 39 packaged YAML files (same names / schema as the reference package) load and build."""
-    RetargetingConfig.set_default_urdf_dir(str(ROBOTS))
+def test_packaged_default_configs_load_with_packaged_urdfs():
+    """The 39 packaged YAML files (same names / schema as the reference package) load and build from the kinematics-only
+    URDFs shipped under dex_retargeting_b200/assets (the real URDF reader, not the JSON fixtures); a path that does not
+    exist raises like the reference (retargeting_config.py:131-132) instead of falling back to anything."""
+    RetargetingConfig.set_default_urdf_dir(str(RetargetingConfig.packaged_urdf_dir()))
+    with pytest.raises(ValueError, match="does not exist"):
+        RetargetingConfig.load_from_file(get_default_config_path(RobotName.allegro, RetargetingType.vector, HandType.right),
+                                         override=dict(urdf_path="allegro_hand/allegro_hand_rigth.urdf"))
     n = 0
     for robot in ROBOT_NAMES:
         for rtype in RetargetingType:
@@ -195,7 +200,7 @@ def test_packaged_default_configs_load_with_fixture_robots():
 def test_step_tol_default_and_env_override(monkeypatch):
     """`Optimizer.step_tol` defaults to 1e-5; DEXR_STEP_TOL (A/B switch) changes the default of
     optimizers constructed afterwards and reaches the launch parameters."""
-    RetargetingConfig.set_default_urdf_dir(str(ROBOTS))
+    RetargetingConfig.set_default_urdf_dir(str(RetargetingConfig.packaged_urdf_dir()))
     path = get_default_config_path(RobotName.allegro, RetargetingType.vector, HandType.right)
     monkeypatch.delenv("DEXR_STEP_TOL", raising=False)
     opt = RetargetingConfig.load_from_file(path).build().optimizer

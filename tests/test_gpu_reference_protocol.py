@@ -77,7 +77,7 @@ def run_protocol(retargeting, vector: bool):
 
 @pytest.fixture(autouse=True)
 def _urdf_dir():
-    RetargetingConfig.set_default_urdf_dir(str(ROBOTS))
+    RetargetingConfig.set_default_urdf_dir(str(RetargetingConfig.packaged_urdf_dir()))
 
 
 @pytest.mark.parametrize("robot_name", ROBOT_NAMES, ids=lambda r: r.name)

@@ -16,7 +16,7 @@ OFFLINE_HANDS = [c for c in ALL_CONFIGS if c.startswith("offline/") and c.endswi
 
 @pytest.fixture(autouse=True)
 def _robots():
-    RetargetingConfig.set_default_urdf_dir(str(ROBOTS))
+    RetargetingConfig.set_default_urdf_dir(str(RetargetingConfig.packaged_urdf_dir()))
 
 
 def test_the_reference_lists_are_covered():

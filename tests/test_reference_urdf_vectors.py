@@ -49,6 +49,17 @@ def test_joint_tree_matches_reference_parser(stem, dummy):
         np.testing.assert_allclose(VEC[f"{tag}/joint_limit"][3:6], [[-2 * np.pi, 2 * np.pi]] * 3)
 
 
+@pytest.mark.parametrize("rel", [str(p) for p in VEC["urdfs"]])
+def test_packaged_urdf_equals_fixture(rel):
+    """The kinematics-only URDFs shipped under dex_retargeting_b200/assets (what bench.py and the default configs load through
+    the real URDF reader) describe exactly the joint trees held to the reference parser above."""
+    from dex_retargeting_b200.retargeting_config import RetargetingConfig
+
+    a = KinematicModel.from_urdf(RetargetingConfig.packaged_urdf_dir() / rel)
+    b = KinematicModel.load(ROBOTS / f"{Path(rel).stem}.json")
+    assert a.to_dict() == b.to_dict()
+
+
 @pytest.mark.parametrize("stem", STEMS)
 @pytest.mark.parametrize("dummy", [False, True])
 def test_dof_set_and_oracle_model_match_reference(stem, dummy):
