@@ -1,0 +1,138 @@
+"""Runtime probe for the REAL reference stack.
+
+pinocchio (pin>=3.3.1) and nlopt (nlopt>=2.8.0) are not installable in the build container, so the oracle restates them
+and is pinned to what can be executed (tests/test_reference_vectors.py, test_reference_urdf_vectors.py,
+test_reference_fk_vectors.py).  On any box where the two packages DO import, this file closes the last link: it runs them
+and holds the oracle and the product's host kinematics to pinocchio itself -- DoF order, frame placements, LOCAL frame
+Jacobians on all 13 hands x {plain, free-flying base} -- and, when the reference package is importable too
+(baseline/_ref, a site-packages install, or a checkout named by DEX_RETARGETING_REFERENCE), runs the reference's own
+`SeqRetargeting.retarget` next to the oracle's restated path.  Skipped (and reported as skipped) where the packages are
+missing; `python tests/test_real_reference.py` prints what was found.
+"""
+import importlib
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, ROBOTS, build_oracle, configs, keypoint_trajectory
+from dex_retargeting_b200.retargeting_config import RetargetingConfig
+from dex_retargeting_b200.robot_wrapper import RobotWrapper
+from dex_retargeting_b200.urdf import KinematicModel
+from oracle.robot import OracleRobot
+
+ROOT = Path(__file__).resolve().parent.parent
+RELS = sorted({Path(c["urdf_path"]).as_posix() for c in configs().values()})
+
+
+def probe():
+    """What of the real reference stack is importable here: {"pinocchio": version|None, "nlopt": ..., "reference": path|None}."""
+    found = {}
+    for name in ("pinocchio", "nlopt"):
+        try:
+            m = importlib.import_module(name)
+            found[name] = getattr(m, "__version__", "unknown")
+        except Exception:
+            found[name] = None
+    found["reference"] = None
+    if found["pinocchio"] and found["nlopt"]:
+        for cand in (os.environ.get("DEX_RETARGETING_REFERENCE"), ROOT / "baseline" / "_ref", "/root/reference/src", None):
+            if cand is not None and not (Path(cand) / "dex_retargeting").exists():
+                continue
+            if cand is not None:
+                sys.path.insert(0, str(cand))
+            try:
+                importlib.import_module("dex_retargeting.seq_retarget")
+                found["reference"] = str(cand) if cand is not None else "site-packages"
+                break
+            except Exception:
+                if cand is not None:
+                    sys.path.remove(str(cand))
+    return found
+
+
+FOUND = probe()
+need_pin = pytest.mark.skipif(not FOUND["pinocchio"], reason="pinocchio is not importable on this box (oracle stays pinned by the reference-executed vectors)")
+need_ref = pytest.mark.skipif(not FOUND["reference"], reason="pinocchio + nlopt + dex_retargeting are not all importable on this box")
+
+
+def test_probe_reports():
+    assert set(FOUND) == {"pinocchio", "nlopt", "reference"}
+    print("real reference stack:", FOUND)
+
+
+def _urdf_for(rel, dummy, tmp_path):
+    """A URDF file pinocchio can load: the packaged kinematics-only URDF, or one with the six dummy joints written out."""
+    src = RetargetingConfig.packaged_urdf_dir() / rel
+    if not dummy:
+        return src
+    dst = tmp_path / (Path(rel).stem + "_dummy.urdf")
+    KinematicModel.from_urdf(src, add_dummy_free_joints=True).write_urdf(dst)
+    return dst
+
+
+@need_pin
+@pytest.mark.parametrize("rel", RELS)
+@pytest.mark.parametrize("dummy", [False, True])
+def test_oracle_and_product_kinematics_equal_pinocchio(rel, dummy, tmp_path):
+    import pinocchio as pin
+
+    path = _urdf_for(rel, dummy, tmp_path)
+    model = pin.buildModelFromUrdf(str(path))          # robot_wrapper.py:15
+    data = model.createData()
+    stem = Path(rel).stem
+    o = OracleRobot(str(ROBOTS / f"{stem}.json"), dummy)
+    r = RobotWrapper(str(ROBOTS / f"{stem}.json"), add_dummy_free_joints=dummy)
+    names = [n for i, n in enumerate(model.names) if model.nqs[i] > 0]    # robot_wrapper.py:33-35
+    assert names == list(o.dof_joint_names) == list(r.dof_joint_names)
+    np.testing.assert_allclose(np.stack([model.lowerPositionLimit, model.upperPositionLimit], 1), o.joint_limits)
+    rng = np.random.RandomState(5)
+    lim = o.joint_limits
+    for _ in range(4):
+        q = rng.uniform(lim[:, 0], lim[:, 1])
+        pin.forwardKinematics(model, data, q)          # :82-83
+        o.compute_forward_kinematics(q)
+        r.compute_forward_kinematics(q)
+        for link in o.link_names:
+            fid = model.getFrameId(link, pin.BODY)     # :61-67
+            T = pin.updateFramePlacement(model, data, fid).homogeneous   # :85-87
+            np.testing.assert_allclose(o.get_link_pose(o.get_link_index(link)), T, atol=1e-12, err_msg=link)
+            np.testing.assert_allclose(r.get_link_pose(r.get_link_index(link)), T, atol=1e-12, err_msg=link)
+            J = pin.computeFrameJacobian(model, data, q, fid)             # :93-95 (LOCAL)
+            np.testing.assert_allclose(r.compute_single_link_local_jacobian(q, r.get_link_index(link)), J, atol=1e-12)
+            Jw = T[:3, :3] @ J[:3]                                         # optimizer.py:172-177
+            o.compute_forward_kinematics(q)
+            np.testing.assert_allclose(o.link_jacobians([o.get_link_index(link)])[0], Jw, atol=1e-12)
+
+
+@need_ref
+@pytest.mark.parametrize("key", ["teleop/allegro_hand_right", "offline/shadow_hand_right", "teleop/leap_hand_right_dexpilot",
+                                 "teleop/schunk_svh_hand_right"])
+def test_reference_stream_next_to_oracle(key):
+    """The reference's own SeqRetargeting (nlopt + pinocchio) on the recorded trajectory next to the oracle's mode-A stream:
+    same objective class (both stop early, SLSQP builds differ), so the bar is the reference's own 1e-2 m task-space bar on
+    the difference plus an objective no worse than 1e-4 apart; and the converged oracle (mode B, the GPU parity target) must
+    not be above the reference's objective."""
+    from dex_retargeting.retargeting_config import RetargetingConfig as RefConfig
+
+    from oracle.solvers import OracleSeqRetargeting
+
+    RefConfig.set_default_urdf_dir(str(RetargetingConfig.packaged_urdf_dir()))
+    ref = RefConfig.from_dict(dict(configs()[key])).build()
+    o = build_oracle(key)
+    seq = OracleSeqRetargeting(o, mode="reference")
+    kp = keypoint_trajectory()[:30]
+    idx = np.asarray(ref.optimizer.target_link_human_indices)
+    worst = 0.0
+    for f in kp:
+        rv = f[idx] if idx.ndim == 1 else f[idx[1]] - f[idx[0]]
+        q_ref = ref.retarget(rv)
+        q_orc = seq.retarget(o.ref_from_keypoints(f))
+        worst = max(worst, float(np.abs(q_ref - q_orc).max()))
+    assert worst < 0.15, f"{key}: reference stream and restated stream differ by {worst:.3e} rad"
+
+
+if __name__ == "__main__":
+    print(FOUND)
