@@ -27,16 +27,10 @@ def find_nvcc() -> str:
 # Experimental builds (csrc/dexr_kernels.cuh, "Experiment switches"): one library per entry under variants/, loaded with
 # DEXR_LIBRARY=<path>.  They are A/B material for tools/ab_variants.sh, never the default.
 VARIANTS = {
-    "smallcode": ["-DDEXR_EXP_SMALLCODE"],
     "fastsincos": ["-DDEXR_EXP_FASTSINCOS"],
-    "smallcode_fastsincos": ["-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_FASTSINCOS"],
     "pdfallback": ["-DDEXR_EXP_PDFALLBACK"],
-    "pdfallback_smallcode": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_SMALLCODE"],
     "fknoise": ["-DDEXR_EXP_FKNOISE"],
     "pdfallback_fknoise": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_FKNOISE"],
-    "all": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_FKNOISE", "-DDEXR_EXP_SMALLCODE", "-DDEXR_EXP_MERGEDRES"],
-    "mergedres": ["-DDEXR_EXP_MERGEDRES"],
-    "mergedres_smallcode": ["-DDEXR_EXP_MERGEDRES", "-DDEXR_EXP_SMALLCODE"],
 }
 
 

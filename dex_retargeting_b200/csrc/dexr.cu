@@ -619,22 +619,15 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (t.dof <= 16) {
     // decoupled 4-joint fingers (Allegro / LEAP vector retargeting): block-diagonal Newton system
-    if (t.block_width == 4) {
-      // DEXR_G16_WARPS=20 / 24: occupancy experiments (102 / 85 registers per thread instead of 128); default 16
-      static const int warps = [] { const char* e = getenv("DEXR_G16_WARPS"); return e ? atoi(e) : 16; }();
-      if (warps == 20) return launch_frames<16, 4, 19>(r, params, io, num_frames, stream);
-      if (warps == 24) return launch_frames<16, 4, 23>(r, params, io, num_frames, stream);
-      return launch_frames<16, 4, 15>(r, params, io, num_frames, stream);
-    }
+    // (20- and 24-warp variants at 96 / 80 registers were measured slower on B200: 1.86e8 / 1.66e8 against 1.89e8 frames/s)
+    if (t.block_width == 4) return launch_frames<16, 4, 15>(r, params, io, num_frames, stream);
     return launch_frames<16, 0, 15>(r, params, io, num_frames, stream);
   }
-  // one frame per warp: 16 warps x 128 registers (small spills) or 12 warps x 168 registers
+  // one frame per warp: 16 warps x 128 registers
   // trunk + decoupled fingers (Shadow hand, any hand on a free-flying base): arrow factorisation
   const bool no_arrow = !arrow_enabled();
   if (t.arrow > 0 && !no_arrow) return launch_frames<32, -1, 15>(r, params, io, num_frames, stream);
-  static const bool wide = [] { const char* e = getenv("DEXR_G32_WARPS"); return !(e && atoi(e) == 12); }();
-  return wide ? launch_frames<32, 0, 15>(r, params, io, num_frames, stream)
-              : launch_frames<32, 0, 11>(r, params, io, num_frames, stream);
+  return launch_frames<32, 0, 15>(r, params, io, num_frames, stream);
 }
 
 template <int G, int BW>

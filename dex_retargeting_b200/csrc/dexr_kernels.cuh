@@ -36,32 +36,24 @@
 
 // Experiment switches (compile time; `python -m dex_retargeting_b200.build --variants` builds one library per switch
 // next to the default one, selected at run time with DEXR_LIBRARY).  The default build defines none of them.
-//   DEXR_EXP_SMALLCODE   keep the short run-time loops of the FK / link placement rolled (smaller LM loop body in
-//                        the instruction cache; the compiler otherwise unrolls them 3-4x with remainder loops)
 //   DEXR_EXP_FASTSINCOS  MUFU sine / cosine (__sincosf, abs. error ~5e-7 on [-pi, pi]) instead of sincosf
 //   DEXR_EXP_PDFALLBACK  when the factorisation of the exact Hessian fails (the kinematic curvature term makes it indefinite
 //                        far from the solution), take that term back out of the stored Hessian and retry at the SAME damping
 //                        with the positive semi-definite model, instead of multiplying the damping by 10 and refactorising
-//                        until it dominates (fp32 solver model: Shadow position 7.7 -> 5.3 iterations, 10.0 -> 5.3
-//                        factorisations per frame; neutral on warm-started streams and unreachable targets)
+//                        until it dominates
 //   DEXR_EXP_FKNOISE     noise floor of the objective for the acceptance test: kNoise |F| PLUS the fp32 resolution of the link
-//                        positions seen through the loss, 2 ulp x sum_k w_k |p_k|_1 (the Huber slope is at most 1).  With
-//                        link positions of ~0.5 m (free-flying base) F ~ 1e-3 is only resolved to ~2e-8, ten times coarser
-//                        than kNoise |F|: a converging Newton step with a predicted decrease of 7e-9 gets rejected on a
-//                        noise bump, the damping escalates, and the frame stops on a damped step 4e-4 rad from the minimiser
-//   DEXR_EXP_MERGEDRES   a residual only touches the joints above its links; residuals that touch disjoint sets of lane
-//                        slots (block mode: the block_width-lane windows; dense mode: 4-lane chunks) are packed into the
-//                        same pass (greedy, once per CTA: SharedTable::pass_res) and every lane works on the residual of
-//                        its slot, instead of all lanes walking all n_res residuals.  Allegro / LEAP vector: 1 pass
-//                        instead of 4; DexPilot on a palm-fixed hand: the wrist -> tip vectors share a pass and disjoint
-//                        finger pairs share passes (about 4 instead of 10).  Hands with wrist joints above every finger
-//                        get no merging (every residual touches the trunk slot).  The terms a lane no longer visits were
-//                        exact zeros: same sums, up to the sign of zero.  Not used in arrow mode or with mimic joints.
-#ifdef DEXR_EXP_SMALLCODE
+//                        positions seen through the loss, 2 ulp x sum_k w_k |p_k|_1 (the Huber slope is at most 1)
+// Two former switches are the default since round 2 (measured on B200, bench workload 1.89e8 -> 2.58e8 frames/s together):
+//   * the short run-time loops of the FK rounds / link placement stay ROLLED (`DEXR_ROLL`): the compiler otherwise unrolls
+//     them 3-4x with remainder loops for trip counts of 1-2, and the LM loop body is instruction-fetch bound;
+//   * MERGED RESIDUAL PASSES: a residual only touches the joints above its links; residuals that touch disjoint sets of lane
+//     slots (block mode: the block_width-lane windows; dense mode: 4-lane chunks) are packed into the same pass (greedy, once
+//     per CTA: SharedTable::pass_res) and every lane works on the residual of its slot, instead of all lanes walking all
+//     n_res residuals.  Allegro / LEAP vector: 1 pass instead of 4; DexPilot on a palm-fixed hand: the wrist -> tip vectors
+//     share a pass and disjoint finger pairs share passes (4 instead of 10).  Hands with wrist joints above every finger get
+//     no merging (every residual touches the trunk slot).  The terms a lane no longer visits were exact zeros: same sums, up
+//     to the sign of zero.  Not used in arrow mode or with mimic joints (one residual per pass there).
 #define DEXR_ROLL _Pragma("unroll 1")
-#else
-#define DEXR_ROLL
-#endif
 
 namespace dexr {
 
@@ -181,12 +173,10 @@ struct SharedTable {
   int group_count[DEXR_MAX_LANES];
   int group_lane[DEXR_MAX_LANES][DEXR_MAX_GROUP];
   float group_mult[DEXR_MAX_LANES][DEXR_MAX_GROUP];
-#ifdef DEXR_EXP_MERGEDRES
   // pass_res[r][slot]: the residual the lanes of `slot` work on in pass r, -1 = none (slot = lane / block_width in block
   // mode, lane / 4 in dense mode)
   int pass_res[DEXR_MAX_RES][DEXR_MAX_LANES / 4];
   int n_pass;
-#endif
 };
 
 __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __restrict__ tb) {
@@ -225,7 +215,6 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
         mx = n > mx ? n : mx;
       }
       st.own_rounds = mx > DEXR_MAX_LINKS_PER_LANE ? DEXR_MAX_LINKS_PER_LANE : mx;
-#ifdef DEXR_EXP_MERGEDRES
       {
         const int gr = tb->block_width > 0 ? tb->block_width : 4;  // lanes per slot
         const int nslot = DEXR_MAX_LANES / 4;
@@ -254,7 +243,6 @@ __device__ inline void load_shared_table(SharedTable& st, const dexr_table_t* __
         }
         st.n_pass = np;
       }
-#endif
     }
     for (int f = 0; f < DEXR_MAX_GROUP; ++f) {
       st.group_lane[i][f] = tb->group_lane[i][f];
@@ -621,25 +609,17 @@ struct Solver {
       const int cb = dense ? 0 : (l & ~(BW - 1));
       const float4* lpc = lp(cur);
       float rmax = 0.f;
-#ifdef DEXR_EXP_MERGEDRES
-      constexpr bool merged = !AR;
-#else
-      constexpr bool merged = false;
-#endif
+      constexpr bool merged = !AR;  // merged residual passes (arrow mode keeps one residual per pass)
       int trips = m;
-#ifdef DEXR_EXP_MERGEDRES
       if constexpr (merged) trips = ST().n_pass;
-#endif
       for (int kk = 0; kk < trips; ++kk) {
         int k = kk;
         bool on = true;  // merged mode: false on the lanes of a slot that has no residual in this pass
-#ifdef DEXR_EXP_MERGEDRES
         if constexpr (merged) {
           const int kw = ST().pass_res[kk][l / (BW > 0 ? BW : 4)];
           on = kw >= 0;
           k = on ? kw : 0;
         }
-#endif
         const int ti = ST().res_task[k], oi = ST().res_origin[k];
         const float4 T = fr()[k];
         const float4 pt = lpc[ti];

@@ -22,8 +22,7 @@ CASES = [  # key, use_arrow, frames
     ("offline/shadow_hand_right", True, 2),          # Solver<32, -1>: position loss, free-flying base (trunk of 8)
     ("teleop/schunk_svh_hand_right", True, 2),       # Solver<32, 0>: 20 lanes, 11 mimic joints
 ]
-VARIANTS = [("DEXR_EXP_SMALLCODE",), ("DEXR_EXP_MERGEDRES",), ("DEXR_EXP_FKNOISE",), ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE"),
-            ("DEXR_EXP_SMALLCODE", "DEXR_EXP_MERGEDRES", "DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE")]
+VARIANTS = [("DEXR_EXP_FKNOISE",), ("DEXR_EXP_PDFALLBACK",), ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE")]
 _cache = {}
 
 
@@ -77,23 +76,13 @@ def test_solver_source_matches_oracle(key, use_arrow, n):
 @pytest.mark.parametrize("defines", VARIANTS, ids=lambda d: "+".join(x.replace("DEXR_EXP_", "").lower() for x in d))
 @pytest.mark.parametrize("key,use_arrow,n", CASES)
 def test_experiment_switches(key, use_arrow, n, defines):
-    """Every compile-time experiment (csrc/dexr_kernels.cuh "Experiment switches") solves the same problems: the rolled
-    loops and the merged residual passes reproduce the default build exactly (same arithmetic, minus terms that are
-    exact zeros; where merging reorders the residuals of a lane -- dense DexPilot -- the sums round differently); the PD
-    fallback takes another iteration path and must land on the oracle's minimiser."""
+    """Every compile-time experiment (csrc/dexr_kernels.cuh "Experiment switches") solves the same problems: the noise
+    floor and the PD fallback take another iteration path and must land on the oracle's minimiser."""
     _, _, _, _, q0, s0, c0, p0 = emulate(key, n, use_arrow)
     o, refs, fixed, x0, q, status, cost, proj = emulate(key, n, use_arrow, defines)
     assert np.all((status >> 24) == 0)
-    reordered = "DEXR_EXP_MERGEDRES" in defines and "dexpilot" in key and use_arrow  # merged passes visit the residuals in
-    path_changing = {"DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE"} & set(defines)  # other acceptance decisions: other iterates
-    if not path_changing and not reordered:                                 # (reordered: same sums, other rounding)
-        np.testing.assert_array_equal(q, q0)
-        np.testing.assert_array_equal(status, s0)
-    elif not path_changing:
-        assert np.abs(q - q0).max() < 1e-5 and np.abs(q - oracle_solutions(key, n)).max() < TOL
-    else:
-        assert np.abs(q - oracle_solutions(key, n)).max() < TOL
-        assert (status & 0xffff).sum() <= (s0 & 0xffff).sum() + 2  # not slower in iterations on these problems
+    assert np.abs(q - oracle_solutions(key, n)).max() < TOL
+    assert (status & 0xffff).sum() <= (s0 & 0xffff).sum() + 2  # not slower in iterations on these problems
     if proj is not None:
         np.testing.assert_array_equal(proj, p0)
 

@@ -186,7 +186,7 @@ def test_block_width_detection():
 
 
 def _pass_schedule(t):
-    """Mirror of the greedy pass scheduler in load_shared_table (csrc/dexr_kernels.cuh, DEXR_EXP_MERGEDRES)."""
+    """Mirror of the greedy pass scheduler in load_shared_table (csrc/dexr_kernels.cuh, merged residual passes)."""
     gr, nslot = (t.block_width if t.block_width > 0 else 4), 8
     merge = not (t.block_width == 0 and t.has_mimic)
     passes, touched = [], []
@@ -210,7 +210,7 @@ def _pass_schedule(t):
 
 
 def test_merged_residual_passes_are_a_valid_schedule():
-    """What the merged residual pass (DEXR_EXP_MERGEDRES, SharedTable::pass_res) relies on, for every shipped configuration:
+    """What the merged residual pass (SharedTable::pass_res) relies on, for every shipped configuration:
     each residual sits in exactly one pass and there owns every lane slot it touches (so all lanes that hold a non-zero
     Jacobian column for it work on it together, and the columns a lane reads belong to its own residual)."""
     counts = {}

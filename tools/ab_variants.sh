@@ -1,10 +1,10 @@
 #!/usr/bin/env bash
 # A/B of the opt-in kernel / solver variants on ONE B200 (run under gpurun; writes gpurun_out/ab/).
 #   gpurun --timeout 1200 -- 'bash tools/ab_variants.sh bench'                 # bench line per variant (~1 min each)
-#   gpurun --timeout 1500 -- 'bash tools/ab_variants.sh verify all'            # GPU suite + all configs under ONE variant
+#   gpurun --timeout 1500 -- 'bash tools/ab_variants.sh verify pdfallback_fknoise'            # GPU suite + all configs under ONE variant
 #   gpurun --timeout 900  -- 'bash tools/ab_variants.sh verify "" DEXR_STEP_TOL=1e-4'   # default library + an env switch
 # Variants: libraries built by `python -m dex_retargeting_b200.build --variants` (compile-time switches, see
-# csrc/dexr_kernels.cuh "Experiment switches") selected with DEXR_LIBRARY, and the run-time switches DEXR_G16_WARPS /
+# csrc/dexr_kernels.cuh "Experiment switches") selected with DEXR_LIBRARY, and the run-time switch
 # DEXR_STEP_TOL.  Nothing printed here is a bench value of record: it picks what becomes the default.
 set -u
 out=gpurun_out/ab
@@ -30,17 +30,12 @@ PY
 case "${1:-bench}" in
 bench)
   bench_one base DEXR_NOP=1
-  for v in smallcode fastsincos mergedres mergedres_smallcode fknoise pdfallback pdfallback_fknoise all; do bench_one "$v" "$(lib $v)"; done
-  for w in 20 24; do
-    bench_one "w$w" DEXR_G16_WARPS=$w
-    bench_one "all_w$w" "$(lib all)" DEXR_G16_WARPS=$w
-  done
+  for v in fastsincos fknoise pdfallback pdfallback_fknoise; do bench_one "$v" "$(lib $v)"; done
   bench_one tol1e-4 DEXR_STEP_TOL=1e-4
-  bench_one all_tol1e-4 "$(lib all)" DEXR_STEP_TOL=1e-4
   # Shadow position / DexPilot / streams are where pdfallback matters: the multi-config table under the two libraries
   python tools/bench_configs.py --out "$out/configs_base.md" > "$out/configs_base.jsonl" 2>&1
-  env "$(lib all)" python tools/bench_configs.py --out "$out/configs_all.md" > "$out/configs_all.jsonl" 2>&1
-  cat "$out/configs_base.md" "$out/configs_all.md"
+  env "$(lib pdfallback_fknoise)" python tools/bench_configs.py --out "$out/configs_pdfallback_fknoise.md" > "$out/configs_pdfallback_fknoise.jsonl" 2>&1
+  cat "$out/configs_base.md" "$out/configs_pdfallback_fknoise.md"
   ;;
 verify)
   v=${2:-}; shift; shift || true
