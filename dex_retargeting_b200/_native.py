@@ -71,7 +71,7 @@ class DexrLaunchInfo(C.Structure):
 
 
 EXPORTS = [
-    "dexr_version", "dexr_last_error", "dexr_table_sizeof", "dexr_params_sizeof", "dexr_default_params",
+    "dexr_version", "dexr_build_id", "dexr_last_error", "dexr_table_sizeof", "dexr_params_sizeof", "dexr_default_params",
     "dexr_robot_create", "dexr_robot_create_from_device", "dexr_robot_device_table", "dexr_robot_destroy",
     "dexr_solve_frames", "dexr_solve_sequences", "dexr_solve_frames_host", "dexr_get_launch_info",
     "dexr_preprocess_keypoints",
@@ -103,6 +103,7 @@ def load():
     lib = C.CDLL(str(path))
     lib.dexr_version.restype = C.c_int
     lib.dexr_last_error.restype = C.c_char_p
+    lib.dexr_build_id.restype = C.c_char_p
     lib.dexr_table_sizeof.restype = C.c_size_t
     lib.dexr_params_sizeof.restype = C.c_size_t
     lib.dexr_default_params.argtypes = [C.POINTER(DexrParams)]
@@ -125,6 +126,11 @@ def load():
         raise DexrError("dexr_params_t layout mismatch between library and binding")
     _LIB = lib
     return lib
+
+
+def build_id() -> str:
+    """The loaded library's source stamp (`dexr_build_id`)."""
+    return load().dexr_build_id().decode()
 
 
 def check(code: int, what: str):

@@ -1,6 +1,7 @@
 """In-tree build of libdexr.so (nvcc, sm_100a only).  `python -m dex_retargeting_b200.build [--force]`"""
 from __future__ import annotations
 
+import hashlib
 import shutil
 import subprocess
 import sys
@@ -34,13 +35,23 @@ VARIANTS = {
 }
 
 
+def source_id(variant: str = "") -> str:
+    """16 hex digits over the library's sources and compile-time switches (what `dexr_build_id()` returns)."""
+    h = hashlib.sha256()
+    for d in DEPS:
+        h.update(d.read_bytes())
+    h.update(" ".join(VARIANTS[variant] if variant else []).encode())
+    return h.hexdigest()[:16]
+
+
 def build_library(force: bool = False, verbose: bool = True, variant: str = "") -> Path:
     out = PKG / "variants" / f"libdexr_{variant}.so" if variant else OUT
     log_path = PKG / "csrc" / (f"build_{variant}.log" if variant else "build.log")
     if not force and out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return out
     out.parent.mkdir(exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, *(VARIANTS[variant] if variant else []), "-o", str(out), str(SRC)]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *(VARIANTS[variant] if variant else []), f'-DDEXR_BUILD_ID="{source_id(variant)}"',
+           "-o", str(out), str(SRC)]
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -336,6 +336,28 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// Every entry point that needs the robot's device current switches to it for the duration of the call only and puts
+// the caller's device back on every exit path (a solve on an optimizer bound to cuda:1 must not move the calling
+// thread's later `device="cuda"` allocations to that GPU).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;  // already current: nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_SCOPE(device)                                                                              \
+  DeviceGuard _dev_guard(device);                                                                          \
+  if (_dev_guard.err != cudaSuccess)                                                                       \
+    return fail(DEXR_E_CUDA, "selecting device %d failed: %s", (int)(device), cudaGetErrorString(_dev_guard.err))
+
 #define CUDA_TRY(expr)                                                                           \
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \
@@ -461,6 +483,10 @@ static int finish_create(dexr_robot* r, dexr_robot_t** out) {
 extern "C" {
 
 int dexr_version(void) { return DEXR_VERSION; }
+#ifndef DEXR_BUILD_ID
+#define DEXR_BUILD_ID "unstamped"
+#endif
+const char* dexr_build_id(void) { return DEXR_BUILD_ID; }
 const char* dexr_last_error(void) { return g_err; }
 size_t dexr_table_sizeof(void) { return sizeof(dexr_table_t); }
 size_t dexr_params_sizeof(void) { return sizeof(dexr_params_t); }
@@ -483,7 +509,7 @@ void dexr_default_params(dexr_params_t* p) {
 int dexr_robot_create(const dexr_table_t* table_host, int device, dexr_robot_t** out) {
   if (!table_host || !out) return fail(DEXR_E_INVALID, "dexr_robot_create: null argument");
   if (int e = validate_table(table_host)) return e;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   dexr_robot* r = new (std::nothrow) dexr_robot();
   if (!r) return fail(DEXR_E_INVALID, "out of host memory");
   r->device = device;
@@ -501,7 +527,7 @@ int dexr_robot_create(const dexr_table_t* table_host, int device, dexr_robot_t**
 int dexr_robot_create_from_device(const void* table_dev, size_t nbytes, int device, dexr_robot_t** out) {
   if (!table_dev || !out) return fail(DEXR_E_INVALID, "dexr_robot_create_from_device: null argument");
   if (nbytes != sizeof(dexr_table_t)) return fail(DEXR_E_INVALID, "table size %zu != %zu", nbytes, sizeof(dexr_table_t));
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   dexr_robot* r = new (std::nothrow) dexr_robot();
   if (!r) return fail(DEXR_E_INVALID, "out of host memory");
   r->device = device;
@@ -525,7 +551,7 @@ const void* dexr_robot_device_table(const dexr_robot_t* robot) { return robot ? 
 
 void dexr_robot_destroy(dexr_robot_t* robot) {
   if (!robot) return;
-  cudaSetDevice(robot->device);
+  DeviceGuard guard(robot->device);
   for (int i = 0; i < 2; ++i) {
     if (robot->streams[i]) cudaStreamDestroy(robot->streams[i]);
     if (robot->stage_dev[i]) cudaFree(robot->stage_dev[i]);
@@ -614,7 +640,7 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
     return fail(DEXR_E_INVALID, "exactly one of keypoints / ref_value must be given");
   if (!io->last_qpos || !io->qpos_out) return fail(DEXR_E_INVALID, "last_qpos and qpos_out are required");
   if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
-  CUDA_TRY(cudaSetDevice(robot->device));
+  DEVICE_SCOPE(robot->device);
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (t.dof <= 16) {
@@ -672,7 +698,7 @@ extern "C" int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params
   const bool use_filter = params->lp_alpha >= 0.f && params->lp_alpha <= 1.f;
   if (use_filter && (!io->filter_state || !io->filter_init)) return fail(DEXR_E_INVALID, "low-pass filter needs filter_state and filter_init");
   if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
-  CUDA_TRY(cudaSetDevice(robot->device));
+  DEVICE_SCOPE(robot->device);
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (t.dof <= 16) {
@@ -691,7 +717,7 @@ int dexr_preprocess_keypoints(const float* raw, float* out, float* wrist_rot_out
   if (!raw || !out) return fail(DEXR_E_INVALID, "dexr_preprocess_keypoints: null argument");
   if (num_frames < 0 || (hand_type != 0 && hand_type != 1)) return fail(DEXR_E_INVALID, "bad num_frames / hand_type");
   if (num_frames == 0) return 0;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const long long tiles = (num_frames + kPreTile - 1) / kPreTile;
@@ -721,7 +747,7 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
   std::lock_guard<std::mutex> lock(robot->mu);
   const dexr_table_t& t = robot->host;
   if (t.n_fixed > 0 && !h->fixed_qpos) return fail(DEXR_E_INVALID, "fixed_qpos is NULL");
-  CUDA_TRY(cudaSetDevice(robot->device));
+  DEVICE_SCOPE(robot->device);
   const int in_row = h->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
   if (!robot->streams[0]) CUDA_TRY(cudaStreamCreateWithFlags(&robot->streams[0], cudaStreamNonBlocking));
   // Zero-copy fast path: when every buffer is page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g.
@@ -765,15 +791,29 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
   auto pad = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t need = pad(chunk * row_in) + pad(chunk * row_last) + pad(chunk * row_fixed) + pad(chunk * row_proj) +
                       pad(chunk * row_q) + pad(chunk * row_rq) + pad(chunk * row_st) + pad(chunk * row_c);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 2; ++i)
     if (!robot->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&robot->streams[i], cudaStreamNonBlocking));
-    if (robot->stage_bytes < need) {
-      if (robot->stage_dev[i]) CUDA_TRY(cudaFree(robot->stage_dev[i]));
+  if (robot->stage_bytes < need) {  // grow both staging buffers, or leave the handle with none (never a stale size)
+    for (int i = 0; i < 2; ++i) {
+      if (robot->stage_dev[i]) cudaFree(robot->stage_dev[i]);
       robot->stage_dev[i] = nullptr;
-      CUDA_TRY(cudaMalloc(&robot->stage_dev[i], need));
     }
+    robot->stage_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+      cudaError_t ce = cudaMalloc(&robot->stage_dev[i], need);
+      if (ce != cudaSuccess) {
+        for (int j = 0; j < 2; ++j) {
+          if (robot->stage_dev[j]) cudaFree(robot->stage_dev[j]);
+          robot->stage_dev[j] = nullptr;
+        }
+        return fail(DEXR_E_CUDA, "allocating %zu staging bytes failed: %s", need, cudaGetErrorString(ce));
+      }
+    }
+    robot->stage_bytes = need;
   }
-  robot->stage_bytes = std::max(robot->stage_bytes, need);
+  // From the first enqueue on, an error must not return while copies / kernels are still in flight on the two internal
+  // streams (they write into the caller's host buffers): run the pipeline in a lambda, drain both streams, then report.
+  auto pipeline = [&]() -> int {
   int ci = 0;
   for (int64_t f0 = 0; f0 < B; f0 += chunk, ci ^= 1) {
     const int64_t n = std::min<int64_t>(chunk, B - f0);
@@ -813,8 +853,14 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
     if (proj) CUDA_TRY(cudaMemcpyAsync(h->projected + f0 * t.len_proj, d_proj, n * row_proj, cudaMemcpyDeviceToHost, s));
     // the staging buffer of this stream is reused two chunks later: same stream => ordered
   }
-  CUDA_TRY(cudaStreamSynchronize(robot->streams[0]));
-  CUDA_TRY(cudaStreamSynchronize(robot->streams[1]));
+  return 0;
+  };
+  const int rc = pipeline();
+  const cudaError_t s0 = cudaStreamSynchronize(robot->streams[0]);
+  const cudaError_t s1 = cudaStreamSynchronize(robot->streams[1]);
+  if (rc != 0) return rc;  // g_err holds the first failure
+  if (s0 != cudaSuccess || s1 != cudaSuccess)
+    return fail(DEXR_E_CUDA, "staged host pipeline failed: %s", cudaGetErrorString(s0 != cudaSuccess ? s0 : s1));
   return 0;
 }
 

@@ -92,6 +92,7 @@ class Optimizer:
         self.idx_pin2fixed = np.array([i for i in range(robot.dof) if i not in idx_pin2target], dtype=int)
         self.opt_dof = len(idx_pin2target)  # includes nothing but the optimised joints
         self.opt = _SolverStats()
+        self.last_status = None  # int32 status words of the most recent host-path solve (iterations | flags)
 
         self.target_link_human_indices = target_link_human_indices
         self.has_free_joint = len([n for n in robot.link_names if "dummy" in n]) >= 6
@@ -121,10 +122,15 @@ class Optimizer:
         return [self.robot.get_link_index(n) for n in target_link_names]
 
     def set_kinematic_adaptor(self, adaptor: KinematicAdaptor):
+        # The reference calls adaptor.forward_qpos / backward_jacobian inside its Python objective (optimizer.py:150-151,
+        # 186-187); here the adaptor is compiled into the robot table, and the only adaptor the reference ships --
+        # the mimic-joint affine map -- is the only one the kernel knows.  Anything else would be silently ignored.
+        if not isinstance(adaptor, MimicJointKinematicAdaptor):
+            raise NotImplementedError(f"{type(adaptor).__name__}: only MimicJointKinematicAdaptor can be compiled into the "
+                                      "robot table of the CUDA solver")
         self.adaptor = adaptor
-        if isinstance(adaptor, MimicJointKinematicAdaptor):  # mimic joints are driven, not supplied
-            mimic = set(int(i) for i in adaptor.idx_pin2mimic)
-            self.idx_pin2fixed = np.array([x for x in self.idx_pin2fixed if int(x) not in mimic], dtype=int)
+        mimic = set(int(i) for i in adaptor.idx_pin2mimic)  # mimic joints are driven, not supplied
+        self.idx_pin2fixed = np.array([x for x in self.idx_pin2fixed if int(x) not in mimic], dtype=int)
         self._engine = None
 
     @property
@@ -228,7 +234,10 @@ class Optimizer:
             io.projected = ptr(projected)
         p = self.params(clip_init=clip_init)
         N.check(eng.lib.dexr_solve_frames_host(eng.handle, C.byref(p), C.byref(io), B), "dexr_solve_frames_host")
-        self.opt._value = float(cost[-1])
+        # nlopt's last_optimum_value() is the reference objective's VALUE, which leaves the regulariser out
+        # (optimizer.py:166-167 vs :194); the kernel's cost includes norm_delta |x - x_last|^2, so take it back out
+        reg = float(self.norm_delta) * float(((qpos[-1].astype(np.float64) - lq[-1].astype(np.float64)) ** 2).sum())
+        self.opt._value = float(cost[-1]) - reg
         self.last_status = status
         return qpos, rq
 

@@ -177,6 +177,10 @@ typedef struct dexr_launch_info {
 } dexr_launch_info_t;
 
 int dexr_version(void);
+/* 16 hex digits: sha256 over the sources this library was compiled from (csrc/dexr.cu, csrc/dexr_kernels.cuh,
+ * include/dexr.h) and the compile-time switches, stamped by dex_retargeting_b200/build.py.  Profiler captures
+ * (profiles/roofline_traffic.json) record it so that a number is never attributed to another binary. */
+const char* dexr_build_id(void);
 const char* dexr_last_error(void);
 size_t dexr_table_sizeof(void);
 size_t dexr_params_sizeof(void);
