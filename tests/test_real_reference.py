@@ -9,8 +9,6 @@ Jacobians on all 13 hands x {plain, free-flying base} -- and, when the reference
 `SeqRetargeting.retarget` next to the oracle's restated path.  Skipped (and reported as skipped) where the packages are
 missing; `python tests/test_real_reference.py` prints what was found.
 """
-import importlib
-import os
 import sys
 from pathlib import Path
 
@@ -24,33 +22,9 @@ from dex_retargeting_b200.urdf import KinematicModel
 from oracle.robot import OracleRobot
 
 ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+from reference_probe import probe  # noqa: E402
 RELS = sorted({Path(c["urdf_path"]).as_posix() for c in configs().values()})
-
-
-def probe():
-    """What of the real reference stack is importable here: {"pinocchio": version|None, "nlopt": ..., "reference": path|None}."""
-    found = {}
-    for name in ("pinocchio", "nlopt"):
-        try:
-            m = importlib.import_module(name)
-            found[name] = getattr(m, "__version__", "unknown")
-        except Exception:
-            found[name] = None
-    found["reference"] = None
-    if found["pinocchio"] and found["nlopt"]:
-        for cand in (os.environ.get("DEX_RETARGETING_REFERENCE"), ROOT / "baseline" / "_ref", "/root/reference/src", None):
-            if cand is not None and not (Path(cand) / "dex_retargeting").exists():
-                continue
-            if cand is not None:
-                sys.path.insert(0, str(cand))
-            try:
-                importlib.import_module("dex_retargeting.seq_retarget")
-                found["reference"] = str(cand) if cand is not None else "site-packages"
-                break
-            except Exception:
-                if cand is not None:
-                    sys.path.remove(str(cand))
-    return found
 
 
 FOUND = probe()
@@ -111,10 +85,10 @@ def test_oracle_and_product_kinematics_equal_pinocchio(rel, dummy, tmp_path):
 @pytest.mark.parametrize("key", ["teleop/allegro_hand_right", "offline/shadow_hand_right", "teleop/leap_hand_right_dexpilot",
                                  "teleop/schunk_svh_hand_right"])
 def test_reference_stream_next_to_oracle(key):
-    """The reference's own SeqRetargeting (nlopt + pinocchio) on the recorded trajectory next to the oracle's mode-A stream:
-    same objective class (both stop early, SLSQP builds differ), so the bar is the reference's own 1e-2 m task-space bar on
-    the difference plus an objective no worse than 1e-4 apart; and the converged oracle (mode B, the GPU parity target) must
-    not be above the reference's objective."""
+    """The reference's own SeqRetargeting (nlopt + pinocchio) on the recorded trajectory next to the oracle's mode-A stream
+    (the restated path: scipy SLSQP at the reference's ftol).  Both stop early and the two SLSQP builds take different
+    line-search steps, so the bar is the accuracy class SURVEY.md section 8c measured for early-stopped iterates
+    (max 0.18 rad from the minimiser), not bit parity."""
     from dex_retargeting.retargeting_config import RetargetingConfig as RefConfig
 
     from oracle.solvers import OracleSeqRetargeting

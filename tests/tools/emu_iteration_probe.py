@@ -17,7 +17,7 @@ import emu_host  # noqa: E402
 from bench_configs import synth  # noqa: E402
 from helpers import build_product  # noqa: E402
 
-VARIANTS = [(), ("DEXR_EXP_FKNOISE",), ("DEXR_EXP_PDFALLBACK", "DEXR_EXP_FKNOISE")]
+VARIANTS = [()]
 
 
 def main(key, B, tol=None):

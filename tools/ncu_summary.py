@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read here, no GPU needed) into a small markdown file for profiles/.
 
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_frames_allegro.md "title"
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r02/frames_allegro.md "title" \
+           [--traffic profiles/roofline_traffic.json --frames 65536 --bytes-per-frame 380 --build-id <dexr_build_id>]
+
+With --traffic, also writes the per-launch figures bench.py turns into `roofline.traffic`, `roofline.issue` and `roofline.fp32`
+(DRAM bytes, warp instructions, FP32 operations = 2 x FFMA + FADD + FMUL thread instructions), stamped with the library build
+id the capture was taken from; bench.py refuses the file when the loaded library reports another id.
 """
 import csv
 import io
@@ -17,11 +22,17 @@ KEYS = [
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "smsp__thread_inst_executed.sum",
 ]
 
 
+def _opt(name, default=None):
+    return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else default
+
+
 def main():
-    rep, out, title = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    rep, out, title = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -57,6 +68,30 @@ def main():
             lines.append(f"| {n} | {v:.0f} |")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    traffic = _opt("--traffic")
+    if traffic:
+        import json
+
+        def val(k, scale=1.0):
+            if k not in col:
+                return None
+            v = float(data[0][col[k]].replace(",", ""))
+            u = units[col[k]]
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            return v * mult * scale
+
+        rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+        ffma, fadd, fmul = (val(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum") for o in ("ffma", "fadd", "fmul"))
+        frames_n, bpf = int(_opt("--frames", "65536")), int(_opt("--bytes-per-frame", "380"))
+        rec = {"build_id": _opt("--build-id"), "kernel": name, "frames_per_launch": frames_n,
+               "dram_bytes_per_launch": None if rd is None else int(rd + wr), "read": rd, "write": wr,
+               "algorithmic_bytes_per_launch": frames_n * bpf, "warp_inst_per_launch": val("smsp__inst_executed.sum"),
+               "fp32_flop_per_launch": None if ffma is None else 2 * ffma + (fadd or 0) + (fmul or 0),
+               "ffma_thread_inst": ffma, "fadd_thread_inst": fadd, "fmul_thread_inst": fmul,
+               "duration_us_under_ncu": val("gpu__time_duration.sum") if "gpu__time_duration.sum" in col else None,
+               "source": f"{out} (ncu --set full, first captured launch)"}
+        open(traffic, "w").write(json.dumps(rec, indent=1) + "\n")
+        print("wrote", traffic)
 
 
 if __name__ == "__main__":
