@@ -78,7 +78,9 @@ constexpr float kLamDown = 0.1f;
 constexpr float kLamUp = 10.0f;
 constexpr float kGradNoise = 1e-7f;  // |dF/dx| below this is indistinguishable from 0 in fp32
 constexpr float kNearStep = 0.1f;    // accepted step (rad / m) below which the exact radial loss curvature is used
-constexpr float kFarResidual = 0.2f; // residual (m) above which the kinematic curvature term is left out
+constexpr float kFarResidual = 1e30f; // (round 1 left the kinematic curvature out beyond 0.2 m because it makes the Hessian indefinite far
+                                     // from the targets; the positive-definite fallback now handles that case, and on targets out of reach
+                                     // the term is what makes the iteration quadratic: 25-60 -> 4-8 iterations)
 constexpr float kTrustDecrease = 0.9f;  // a trusted step counts as progress when the gradient max-norm shrank below this factor
 
 // ------------------------------------------------------------------------------------------------
@@ -574,14 +576,15 @@ struct Solver {
     int rechecks = 0;
     unsigned last_fmask = 0u;
     // Steps whose predicted decrease is below what fp32 resolves in F are taken on trust; whether they were any good is read
-    // off the GRADIENT one iteration later (it is computed directly, not by differencing F, and resolves far below the
-    // noise of F): a smaller gradient relaxes the damping like a verified decrease would, two trusted steps in a row
-    // without a smaller gradient mean the KKT residual sits at its fp32 floor and the frame ends there.
-    // A trusted step that made the gradient LARGER marks the local model as unreliable (seen on targets far out of reach: a
-    // two-cycle between a relaxed, overshooting step and a damped one): the damping is then only relaxed again after a
-    // decrease of F that fp32 can resolve.
-    float gn_prev = 0.f;
-    bool trust_prev = false, relax_ok = true;
+    // off the GRADIENT one iteration later (it is computed directly, not by differencing F, and resolves far below the noise
+    // of F).  A smaller gradient max-norm keeps the step and relaxes the damping like a verified decrease would.  A gradient
+    // that did not shrink REVERTS the step: the next trial is forced back to the previous point (x_prev; the forward
+    // kinematics and the objective terms are re-evaluated through the ordinary trial code) and the damping goes up, so the
+    // gradient norm is monotone over trusted steps -- no cycling between an overshooting and a damped step (seen on targets
+    // far out of reach), no creeping at a damping collected early (round 1: 583 of 614 400 DexPilot stream frames ran into
+    // max_iters).  Two reverts in a row mean the KKT residual sits at its fp32 floor: the frame ends at the best point.
+    float gn_prev = 0.f, x_prev = 0.f;
+    bool trust_prev = false;
     int stall = 0;
 
     // ---- arrow mode: this lane's finger window (see the Solver comment); loop invariant ----
@@ -829,16 +832,17 @@ struct Solver {
       }
       if (!free_) g = 0.f;
       const float gn = gmax<G>(fabsf(g));
+      bool revert = false;
       if (trust_prev && !done) {
-        if (gn < kTrustDecrease * gn_prev) {
-          if (relax_ok) lam = fmaxf(lam * kLamDown, kLamMin);
+        if (gn < gn_prev) {
+          if (gn < kTrustDecrease * gn_prev) lam = fmaxf(lam * kLamDown, kLamMin);
           stall = 0;
-        } else if (gn >= gn_prev) {
-          relax_ok = false;
-          if (++stall >= 2) { done = true; status |= DEXR_STATUS_NOISEFLOOR; }
+        } else {
+          revert = true;
+          ++stall;
         }
       }
-      DEXR_TRACE_PRINT("  it %2d gn %.3e gn_prev %.3e trust_prev %d stall %d lam %.1e\n", iters, gn, gn_prev, (int)trust_prev, stall, lam);
+      DEXR_TRACE_PRINT("  it %2d gn %.3e gn_prev %.3e trust_prev %d stall %d revert %d lam %.1e\n", iters, gn, gn_prev, (int)trust_prev, stall, (int)revert, lam);
       float* hbuf = hb();
 #pragma unroll
       for (int i = 0; i < HN; ++i) hbuf[i * NP + l] = H[i];
@@ -1032,7 +1036,7 @@ struct Solver {
           if (l == pk) y = xk;
           if (l < pk) y = fmaf(-Lc[(l - cb) * (NP + 1) + pk], xk, y);
         }
-        bad = gany<G>(bad || !isfinite(y), lane);
+        bad = gany<G>(bad || !isfinite(y), lane) && !revert;  // a reverting group ignores this factorisation
         bool dropped = false;  // this group took the kinematic curvature out in this trial: retry at the same damping
         {
           const bool drop = bad && !accepted && curv_in;
@@ -1071,6 +1075,7 @@ struct Solver {
         }
         float xn = free_ ? fminf(fmaxf(x + y, lo), hi) : x;
         if (bad) xn = x;
+        if (revert) xn = x_prev;  // (every lane: the variable set that was free during the reverted step may differ)
         const float dx = xn - x;
         const float step = gmax<G>(fabsf(dx));
         const float pred = 0.5f * gsum<G>(dx * fmaf(lam * D, dx, -g));
@@ -1085,14 +1090,15 @@ struct Solver {
         const float dF = gsum<G>(cost_lane - Fl);
         const float fnoise = fmaf(kNoise, fabsf(F), 2.4e-7f * fmaxf(Fnz, cost_nz));
         // a step taken on trust must at least not raise F by more than its noise
-        const bool ok = !bad && isfinite(Fn) && (dF <= 0.f || ((step < prm.tol || pred < fnoise) && dF <= fnoise));
+        const bool ok = revert || (!bad && isfinite(Fn) && (dF <= 0.f || ((step < prm.tol || pred < fnoise) && dF <= fnoise)));
         // the damping is relaxed after a decrease that fp32 can resolve: one beyond the worst-case rounding bound, or one that
         // agrees with the quadratic model's prediction to within a half (rounding noise that large would not track it)
-        const bool verified = dF < -fnoise || (dF < 0.f && fabsf(dF + pred) <= 0.5f * pred);
+        const bool verified = !revert && (dF < -fnoise || (dF < 0.f && fabsf(dF + pred) <= 0.5f * pred));
         DEXR_TRACE_PRINT("  it %2d trial %d lam %.1e exact %d step %.3e pred %.3e F %.9e Fn %.9e dF %.2e noise %.1e bad %d ok %d ver %d fmask %x\n", iters,
                          trial, lam, (int)exact, step, pred, F, Fn, dF, fnoise, (int)bad, (int)ok, (int)verified, fmask);
         if (!accepted) {
           if (ok) {
+            x_prev = x;
             x = xn; q = qn; F = Fn;
             Fnz = cost_nz;
             Fl = cost_lane;
@@ -1102,12 +1108,20 @@ struct Solver {
             for (int i = 0; i < 3; ++i) p[i] = pn[i];
             cur ^= 1;
             if (verified) lam = fmaxf(lam * kLamDown, kLamMin);
-            trust_prev = !verified;
-            if (verified) { stall = 0; relax_ok = true; }
+            // fnoise is a worst-case bound (every rounding error with the same sign); a decrease beyond an eighth of it is
+            // already unlikely to be noise: such a step is kept whatever the next gradient says (it just does not relax
+            // the damping).  Only steps whose effect on F is truly unresolved are put to the gradient test.
+            trust_prev = !verified && !revert && !(dF < -0.125f * fnoise);
+            if (verified) stall = 0;
             gn_prev = gn;
             accepted = true;
             acc_step = step;
-            if (step < prm.tol) {
+            if (revert) {  // back at the previous point: more damping, or the end when this is the second revert in a row
+              lam *= kLamUp;
+              ++rejects;
+              if (stall >= 2) { done = true; status |= DEXR_STATUS_NOISEFLOOR; }
+              revert = false;
+            } else if (step < prm.tol) {
               if (any_act) recheck = true;
               else done = true;
             }
