@@ -65,6 +65,15 @@ class DexrSequences(C.Structure):
     ]
 
 
+class DexrGroup(C.Structure):
+    """Mirror of `dexr_group_t`: one (robot, batch) group of a mixed-robot launch."""
+
+    _fields_ = [("robot", C.c_void_p), ("params", C.POINTER(DexrParams)), ("io", DexrFrames), ("num_frames", C.c_int64)]
+
+
+MAX_GROUPS = 16
+
+
 class DexrLaunchInfo(C.Structure):
     _fields_ = [("grid", _i), ("block", _i), ("smem_bytes", _i), ("frames_per_tile", _i), ("lanes_per_frame", _i),
                 ("consumer_warps", _i), ("kernels_launched", _i)]
@@ -73,7 +82,7 @@ class DexrLaunchInfo(C.Structure):
 EXPORTS = [
     "dexr_version", "dexr_build_id", "dexr_last_error", "dexr_table_sizeof", "dexr_params_sizeof", "dexr_default_params",
     "dexr_robot_create", "dexr_robot_create_from_device", "dexr_robot_device_table", "dexr_robot_destroy",
-    "dexr_solve_frames", "dexr_solve_sequences", "dexr_solve_frames_host", "dexr_get_launch_info",
+    "dexr_solve_frames", "dexr_solve_frames_multi", "dexr_solve_sequences", "dexr_solve_frames_host", "dexr_get_launch_info",
     "dexr_preprocess_keypoints",
 ]
 
@@ -115,6 +124,7 @@ def load():
     lib.dexr_robot_destroy.argtypes = [C.c_void_p]
     lib.dexr_robot_destroy.restype = None
     lib.dexr_solve_frames.argtypes = [C.c_void_p, C.POINTER(DexrParams), C.POINTER(DexrFrames), C.c_int64, C.c_void_p]
+    lib.dexr_solve_frames_multi.argtypes = [C.POINTER(DexrGroup), C.c_int32, C.c_void_p]
     lib.dexr_solve_sequences.argtypes = [C.c_void_p, C.POINTER(DexrParams), C.POINTER(DexrSequences), C.c_int64,
                                          C.c_int64, C.c_void_p]
     lib.dexr_solve_frames_host.argtypes = [C.c_void_p, C.POINTER(DexrParams), C.POINTER(DexrFrames), C.c_int64]

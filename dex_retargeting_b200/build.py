@@ -29,6 +29,7 @@ def find_nvcc() -> str:
 # DEXR_LIBRARY=<path>.  They are A/B material for tools/ab_variants.sh, never the default.
 VARIANTS = {
     "fastsincos": ["-DDEXR_EXP_FASTSINCOS"],
+    "multi_calls": ["-DDEXR_EXP_MULTI_CALLS"],
 }
 
 

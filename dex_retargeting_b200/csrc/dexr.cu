@@ -46,8 +46,11 @@ struct SeqArgs {
 // ------------------------------------------------------------------------------------------------
 // independent frames: producer warp (TMA ring) + NCW consumer warps
 // ------------------------------------------------------------------------------------------------
+// One robot group, executed by one CTA: the tiles `first_tile, first_tile + gridDim.x, ...` of the group's batch.  Both the
+// single-robot kernel and the mixed-robot kernel (several groups back to back inside one launch) run this body; it starts
+// and ends with a CTA-wide barrier, so it can be called repeatedly with different tables / template parameters.
 template <int G, int BW, int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const FrameArgs a) {
+__device__ __forceinline__ void frames_group(const FrameArgs& a, int first_tile) {
   unsigned char* const smem = dsmem;
   SharedTable* st = reinterpret_cast<SharedTable*>(smem);
   unsigned char* ring = smem + a.ring_off;
@@ -55,6 +58,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
   uint64_t* empty = full + 2;
   int* next = reinterpret_cast<int*>(empty + 2);
 
+  __syncthreads();  // (mixed launches: every warp is done with the previous group's table, ring and barriers)
   load_shared_table(*st, a.table);
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
   if (warp == NCW) {
     // ===================== producer: stage tiles HBM -> shared memory =====================
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int stage = it & 1;
       if (it >= 2) mbar_wait(&empty[stage], ((it >> 1) - 1) & 1);
       const long long f0 = (long long)tile * a.T;
@@ -109,52 +113,100 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const Fr
       }
       __syncwarp();
     }
-    return;
-  }
+  } else {
+    // ===================== consumers: one frame per group of G lanes =========================
+    constexpr int GPW = 32 / G;
+    const int gid = warp * GPW + (lane / G);
+    Solver<G, BW> sv;
+    sv.init(a.table, a.dm, (uint32_t)(a.scratch_off + gid * Scratch<G>::kFloats * 4), a.prm, lane);
 
-  // ===================== consumers: one frame per group of G lanes =========================
-  constexpr int GPW = 32 / G;
-  const int gid = warp * GPW + (lane / G);
-  Solver<G, BW> sv;
-  sv.init(a.table, a.dm, (uint32_t)(a.scratch_off + gid * Scratch<G>::kFloats * 4), a.prm, lane);
-
-  int it = 0;
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
-    mbar_wait(&full[stage], (it >> 1) & 1);
-    const long long f0 = (long long)tile * a.T;
-    const int count = (int)min((long long)a.T, a.B - f0);
-    const unsigned char* sb = ring + stage * a.stage_bytes;
-    const float* s_in = reinterpret_cast<const float*>(sb + a.off_in);
-    const float* s_last = reinterpret_cast<const float*>(sb + a.off_last);
-    const float* s_fixed = reinterpret_cast<const float*>(sb + a.off_fixed);
-    while (true) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&next[stage], GPW);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= count) break;
-      const int idx = base + (lane / G);
-      const bool active = idx < count;
-      const int ci = active ? idx : base;
-      const long long f = f0 + ci;
-      FrameInputs in;
-      in.kp = by_kp ? s_in + ci * a.in_row : nullptr;
-      in.ref = by_kp ? nullptr : s_in + ci * a.in_row;
-      in.last = s_last + ci * a.dm.n_var;
-      in.fixed = s_fixed + ci * a.dm.n_fixed;
-      in.projected = a.io.projected ? a.io.projected + f * a.dm.len_proj : nullptr;
-      const int status = sv.solve(in, active);
-      if (active) {
-        if (sv.var >= 0) a.io.qpos_out[f * a.dm.n_var + sv.var] = sv.x;
-        if (a.io.robot_qpos_out && sv.l < a.dm.dof) a.io.robot_qpos_out[f * a.dm.dof + sv.l] = sv.q;
-        if (sv.l == 0) {
-          if (a.io.status_out) a.io.status_out[f] = status;
-          if (a.io.cost_out) a.io.cost_out[f] = sv.F;
+    int it = 0;
+    for (int tile = first_tile; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int stage = it & 1;
+      mbar_wait(&full[stage], (it >> 1) & 1);
+      const long long f0 = (long long)tile * a.T;
+      const int count = (int)min((long long)a.T, a.B - f0);
+      const unsigned char* sb = ring + stage * a.stage_bytes;
+      const float* s_in = reinterpret_cast<const float*>(sb + a.off_in);
+      const float* s_last = reinterpret_cast<const float*>(sb + a.off_last);
+      const float* s_fixed = reinterpret_cast<const float*>(sb + a.off_fixed);
+      while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&next[stage], GPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const int idx = base + (lane / G);
+        const bool active = idx < count;
+        const int ci = active ? idx : base;
+        const long long f = f0 + ci;
+        FrameInputs in;
+        in.kp = by_kp ? s_in + ci * a.in_row : nullptr;
+        in.ref = by_kp ? nullptr : s_in + ci * a.in_row;
+        in.last = s_last + ci * a.dm.n_var;
+        in.fixed = s_fixed + ci * a.dm.n_fixed;
+        in.projected = a.io.projected ? a.io.projected + f * a.dm.len_proj : nullptr;
+        const int status = sv.solve(in, active);
+        if (active) {
+          if (sv.var >= 0) a.io.qpos_out[f * a.dm.n_var + sv.var] = sv.x;
+          if (a.io.robot_qpos_out && sv.l < a.dm.dof) a.io.robot_qpos_out[f * a.dm.dof + sv.l] = sv.q;
+          if (sv.l == 0) {
+            if (a.io.status_out) a.io.status_out[f] = status;
+            if (a.io.cost_out) a.io.cost_out[f] = sv.F;
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
+  }
+}
+
+template <int G, int BW, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_kernel(const FrameArgs a) {
+  frames_group<G, BW, NCW>(a, blockIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mixed robots: ONE persistent launch over a list of (robot table, frame batch) groups (the reference builds one optimizer
+// per robot, retargeting_config.py:167-257, and would run them one after the other).  A CTA walks the groups in order; per
+// group it reloads the 8 KB table into shared memory and re-arms the input ring (two CTA barriers), picks the solver
+// instantiation the table asks for (16 / 32 lanes, block / dense / arrow Hessian) and takes every gridDim-th tile.  The
+// round-robin over CTAs continues ACROSS groups (`rot`), so the CTAs that got one tile fewer in one group are first in line
+// in the next.  There is no grid-wide barrier: a CTA that finishes a group early starts the next one, and the only tail
+// of the launch is the last group's.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxGroups = DEXR_MAX_GROUPS;
+struct MultiArgs {
+  int n_groups;
+  int kind[kMaxGroups];  // 0: <16,4>  1: <16,0>  2: <32,-1>  3: <32,0>
+  FrameArgs g[kMaxGroups];
+};
+
+// A/B switch DEXR_EXP_MULTI_CALLS: a real call per solver instantiation (own register allocation per body, but the group's
+// arguments then come through a pointer instead of the constant bank) instead of four inlined bodies in one allocation.
+template <int G, int BW, int NCW>
+#ifdef DEXR_EXP_MULTI_CALLS
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void frames_group_call(const FrameArgs& a, int first_tile) {
+  frames_group<G, BW, NCW>(a, first_tile);
+}
+
+template <int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) dexr_frames_multi_kernel(const __grid_constant__ MultiArgs m) {
+  int rot = 0;  // tiles handed out so far, modulo the grid: where the round-robin continues
+  for (int gi = 0; gi < m.n_groups; ++gi) {
+    const FrameArgs& a = m.g[gi];
+    const int first = (int)((blockIdx.x + gridDim.x - rot) % gridDim.x);
+    switch (m.kind[gi]) {
+      case 0: frames_group_call<16, 4, NCW>(a, first); break;
+      case 1: frames_group_call<16, 0, NCW>(a, first); break;
+      case 2: frames_group_call<32, -1, NCW>(a, first); break;
+      default: frames_group_call<32, 0, NCW>(a, first); break;
+    }
+    rot = (rot + a.ntiles) % gridDim.x;
   }
 }
 
@@ -589,17 +641,18 @@ static bool arrow_enabled() {
   return !(e && atoi(e) == 0);
 }
 
-template <int G, int BW, int NCW>
-static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+// Fill the kernel arguments of one robot group: tile size, ring layout, dynamic shared memory.  `slots` = CTAs the tiles are
+// spread over.  Returns the dynamic shared memory the group needs.
+template <int G, int NCW>
+static int fill_frame_args(const dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, int slots, FrameArgs& a) {
   const dexr_table_t& t = r->host;
-  FrameArgs a{};
+  a = FrameArgs{};
   a.table = r->table_dev;
   a.prm = *prm;
   a.io = *io;
   a.B = B;
   a.dm = make_dims(t);
   a.in_row = io->keypoints ? 3 * DEXR_NUM_KEYPOINTS : 3 * t.n_res;
-  const int slots = r->num_sms;  // one CTA per SM
   long long per = (B + slots - 1) / slots;
   int T = (int)std::min<long long>(FramesCfg<G>::kMaxTile, std::max<long long>(4, per));
   T = round_up(T, 4);
@@ -616,7 +669,14 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   a.bar_off = a.ring_off + 2 * a.stage_bytes;
   a.scratch_off = round_up(a.bar_off + 4 * 8 + 2 * 4, 16);
   constexpr int GPW = 32 / G;
-  const int smem = a.scratch_off + NCW * GPW * Scratch<G>::kFloats * 4;
+  return a.scratch_off + NCW * GPW * Scratch<G>::kFloats * 4;
+}
+
+template <int G, int BW, int NCW>
+static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+  FrameArgs a;
+  const int slots = r->num_sms;  // one CTA per SM
+  const int smem = fill_frame_args<G, NCW>(r, prm, io, B, slots, a);
   auto kern = dexr_frames_kernel<G, BW, NCW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(a.ntiles, slots);
@@ -624,7 +684,61 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   CUDA_TRY(cudaGetLastError());
   {
     std::lock_guard<std::mutex> lk(r->info_mu);
-    r->last = dexr_launch_info_t{grid, (NCW + 1) * 32, smem, T, G, NCW, r->last.kernels_launched + 1};
+    r->last = dexr_launch_info_t{grid, (NCW + 1) * 32, smem, a.T, G, NCW, r->last.kernels_launched + 1};
+  }
+  return 0;
+}
+
+// Which solver instantiation a table runs on: 0 <16,4> block diagonal, 1 <16,0> dense, 2 <32,-1> arrow, 3 <32,0> dense.
+static int solver_kind(const dexr_table_t& t) {
+  if (t.dof <= 16) return t.block_width == 4 ? 0 : 1;
+  return (t.arrow > 0 && arrow_enabled()) ? 2 : 3;
+}
+
+static int check_frames_io(const dexr_table_t& t, const dexr_frames_t* io) {
+  if ((io->keypoints != nullptr) == (io->ref_value != nullptr))
+    return fail(DEXR_E_INVALID, "exactly one of keypoints / ref_value must be given");
+  if (!io->last_qpos || !io->qpos_out) return fail(DEXR_E_INVALID, "last_qpos and qpos_out are required");
+  if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
+  return 0;
+}
+
+extern "C" int dexr_solve_frames_multi(const dexr_group_t* groups, int32_t num_groups, void* cuda_stream) {
+  if (!groups) return fail(DEXR_E_INVALID, "dexr_solve_frames_multi: null argument");
+  if (num_groups < 0 || num_groups > DEXR_MAX_GROUPS) return fail(DEXR_E_INVALID, "num_groups %d out of range 0..%d", num_groups, DEXR_MAX_GROUPS);
+  constexpr int NCW = 15;
+  MultiArgs m{};
+  int smem = 0, device = -1, sms = 0;
+  long long tiles = 0;
+  dexr_robot* first = nullptr;
+  for (int i = 0; i < num_groups; ++i) {
+    const dexr_group_t& g = groups[i];
+    if (!g.robot || !g.params) return fail(DEXR_E_INVALID, "group %d: null robot / params", i);
+    if (g.num_frames < 0) return fail(DEXR_E_INVALID, "group %d: num_frames < 0", i);
+    if (g.num_frames == 0) continue;
+    if (int e = check_params(g.params)) return e;
+    dexr_robot* r = const_cast<dexr_robot*>(g.robot);
+    if (int e = check_frames_io(r->host, &g.io)) return e;
+    if (device < 0) { device = r->device; sms = r->num_sms; first = r; }
+    if (r->device != device) return fail(DEXR_E_INVALID, "group %d lives on device %d, group 0 on device %d: one launch, one device", i, r->device, device);
+    const int k = solver_kind(r->host);
+    FrameArgs& a = m.g[m.n_groups];
+    const int need = k <= 1 ? fill_frame_args<16, NCW>(r, g.params, &g.io, g.num_frames, sms, a)
+                            : fill_frame_args<32, NCW>(r, g.params, &g.io, g.num_frames, sms, a);
+    smem = std::max(smem, need);
+    m.kind[m.n_groups++] = k;
+    tiles += a.ntiles;
+  }
+  if (m.n_groups == 0) return 0;
+  DEVICE_SCOPE(device);
+  auto kern = dexr_frames_multi_kernel<NCW>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = (int)std::min<long long>(tiles, sms);
+  kern<<<grid, (NCW + 1) * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(m);
+  CUDA_TRY(cudaGetLastError());
+  {
+    std::lock_guard<std::mutex> lk(first->info_mu);
+    first->last = dexr_launch_info_t{grid, (NCW + 1) * 32, smem, m.g[0].T, 0, NCW, first->last.kernels_launched + 1};
   }
   return 0;
 }
@@ -636,10 +750,7 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   if (num_frames == 0) return 0;
   if (int e = check_params(params)) return e;
   const dexr_table_t& t = robot->host;
-  if ((io->keypoints != nullptr) == (io->ref_value != nullptr))
-    return fail(DEXR_E_INVALID, "exactly one of keypoints / ref_value must be given");
-  if (!io->last_qpos || !io->qpos_out) return fail(DEXR_E_INVALID, "last_qpos and qpos_out are required");
-  if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
+  if (int e = check_frames_io(t, io)) return e;
   DEVICE_SCOPE(robot->device);
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);

@@ -433,7 +433,8 @@ struct Solver {
 
   // Objective L(x) + norm_delta |x - x0|^2 from link buffer b (value part of optimizer.py:162-167,
   // 263-274, 524-541, with the regulariser the reference only puts into the gradient).
-  __device__ __forceinline__ float cost(int b, float xv) const {
+  // Sets cost_lane (this lane's term) and cost_nz (group sum of the noise scale); the caller sums what it needs.
+  __device__ __forceinline__ void cost(int b, float xv) const {
     float v = 0.f;
     float nz = 0.f;
     const int m = dm.n_res;
@@ -466,7 +467,6 @@ struct Solver {
     }
     cost_lane = v;
     cost_nz = gsum<G>(nz);
-    return gsum<G>(v);
   }
 
   // Per-frame targets and weights -> fr[k]; DexPilot flag update (optimizer.py:460-508).
@@ -559,9 +559,10 @@ struct Solver {
     write_world_links();
     write_links(R, p, cur);
     __syncwarp();
-    F = cost(cur, x);
+    cost(cur, x);
     Fnz = cost_nz;
     Fl = cost_lane;
+    F = gsum<G>(Fl);
 
     float lam = prm.lambda0;
     int iters = 0, rejects = 0;
@@ -1083,11 +1084,12 @@ struct Solver {
         fk(qn, Rn, pn);
         write_links(Rn, pn, cur ^ 1);
         __syncwarp();
-        const float Fn = cost(cur ^ 1, xn);
+        cost(cur ^ 1, xn);
         // F(xn) - F(x) summed term by term: every lane differences its own residual / regulariser term (nearby numbers: the
         // subtraction is exact), so the result carries the rounding of the terms -- a few ulp of each -- and of the link
         // positions behind them, not ulp(F)
         const float dF = gsum<G>(cost_lane - Fl);
+        const float Fn = F + dF;  // (a few ulp of drift per accepted step; F only scales the noise floor and is reported)
         const float fnoise = fmaf(kNoise, fabsf(F), 2.4e-7f * fmaxf(Fnz, cost_nz));
         // a step taken on trust must at least not raise F by more than its noise
         const bool ok = revert || (!bad && isfinite(Fn) && (dF <= 0.f || ((step < prm.tol || pred < fnoise) && dF <= fnoise)));

@@ -305,6 +305,20 @@ class Optimizer:
         Returns qpos [B,opt_dof] (= `out` if given).  Nothing is synchronised."""
         import torch
 
+        eng, io, p, out, B = self._prepare_batch(ref_value, fixed_qpos, last_qpos, keypoints=keypoints, projected=projected, out=out,
+                                                 robot_qpos_out=robot_qpos_out, status_out=status_out, cost_out=cost_out,
+                                                 clip_init=clip_init)
+        s = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", eng.device))
+        N.check(eng.lib.dexr_solve_frames(eng.handle, C.byref(p), C.byref(io), B, C.c_void_p(s.cuda_stream)),
+                "dexr_solve_frames")
+        return out
+
+    def _prepare_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None, out=None,
+                       robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False):
+        """Validate the tensors of one batch and lay them out as `dexr_frames_t` (shared by the single-robot and the
+        mixed-robot launch).  Returns (engine, io, params, out, B)."""
+        import torch
+
         eng = self.engine()
         if last_qpos is None:
             raise ValueError("last_qpos is required")
@@ -342,11 +356,35 @@ class Optimizer:
             io.cost_out = chk(cost_out, (B,), torch.float32, "cost_out")
         if projected is not None:
             io.projected = chk(projected, (B, self._objective_spec().len_proj), torch.uint8, "projected")
-        s = stream if stream is not None else torch.cuda.current_stream(dev)
-        p = self.params(clip_init=clip_init)
-        N.check(eng.lib.dexr_solve_frames(eng.handle, C.byref(p), C.byref(io), B, C.c_void_p(s.cuda_stream)),
-                "dexr_solve_frames")
-        return out
+        return eng, io, self.params(clip_init=clip_init), out, B
+
+
+def retarget_batch_mixed(jobs, stream=None):
+    """Several robots, ONE launch (`dexr_solve_frames_multi`): `jobs` is a list of `(optimizer, kwargs)` where `kwargs` are the
+    arguments of `Optimizer.retarget_batch` for that robot's batch (every optimizer on the same device, at most 16 groups).
+    The reference builds one optimizer per robot and would run them back to back (retargeting_config.py:167-257); here a CTA
+    walks the groups inside one persistent kernel, reloading the 8 KB robot table between groups, so small per-robot batches
+    do not each pay a launch and a tail.  Returns the list of result tensors, bit-identical to per-robot launches."""
+    import torch
+
+    if len(jobs) > N.MAX_GROUPS:
+        raise ValueError(f"at most {N.MAX_GROUPS} robot groups per launch, got {len(jobs)}")
+    groups = (N.DexrGroup * max(len(jobs), 1))()
+    keep, outs, dev_index = [], [], None
+    for i, (opt, kw) in enumerate(jobs):
+        eng, io, p, out, B = opt._prepare_batch(**kw)
+        if dev_index is None:
+            dev_index = eng.device
+        elif eng.device != dev_index:
+            raise ValueError("all robots of a mixed launch must live on the same device")
+        keep.append((eng, p))
+        groups[i].robot, groups[i].params, groups[i].io, groups[i].num_frames = eng.handle, C.pointer(p), io, B
+        outs.append(out)
+    if not jobs:
+        return outs
+    s = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", dev_index))
+    N.check(N.load().dexr_solve_frames_multi(groups, len(jobs), C.c_void_p(s.cuda_stream)), "dexr_solve_frames_multi")
+    return outs
 
 
 class PositionOptimizer(Optimizer):

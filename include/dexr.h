@@ -29,6 +29,7 @@ extern "C" {
 
 #define DEXR_MAX_LANES 32  /* movable joints (pinocchio DoFs incl. mimic + dummy), one per lane   */
 #define DEXR_MAX_LINKS 16  /* links whose position enters the objective                             */
+#define DEXR_MAX_GROUPS 16 /* robot groups per mixed launch (dexr_solve_frames_multi)                     */
 #define DEXR_MAX_RES 16    /* residual blocks: vectors (vector / dexpilot) or points (position)     */
 #define DEXR_MAX_GROUP 4   /* joints driven by one optimisation variable (itself + mimic joints)    */
 #define DEXR_MAX_LINKS_PER_LANE 4 /* objective links rigidly attached to the same movable joint        */
@@ -202,6 +203,16 @@ void dexr_robot_destroy(dexr_robot_t* robot);
 /* Independent frames: replaces B calls of Optimizer.retarget() (optimizer.py:77-102). */
 int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t* params, const dexr_frames_t* io,
                       int64_t num_frames, void* cuda_stream);
+/* Mixed robots: several (robot, batch) groups solved by ONE persistent launch -- replaces one Optimizer per robot run one
+ * after the other (retargeting_config.py:167-257 builds exactly one optimizer per config).  Every group has its own table,
+ * parameters and buffers (all on the same device); results are bit-identical to one dexr_solve_frames call per group. */
+typedef struct dexr_group {
+  const dexr_robot_t* robot;
+  const dexr_params_t* params;
+  dexr_frames_t io;
+  int64_t num_frames;
+} dexr_group_t;
+int dexr_solve_frames_multi(const dexr_group_t* groups, int32_t num_groups, void* cuda_stream);
 /* Streams: replaces S x T calls of SeqRetargeting.retarget() (seq_retarget.py:112-134). */
 int dexr_solve_sequences(const dexr_robot_t* robot, const dexr_params_t* params, const dexr_sequences_t* io,
                          int64_t num_streams, int64_t num_steps, void* cuda_stream);
