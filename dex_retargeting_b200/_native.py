@@ -46,7 +46,7 @@ class DexrParams(C.Structure):
     _fields_ = [
         ("huber_delta", _f), ("norm_delta", _f), ("scaling", _f), ("project_dist", _f), ("escape_dist", _f),
         ("eta1", _f), ("eta2", _f), ("lp_alpha", _f), ("tol", _f), ("lambda0", _f),
-        ("max_iters", _i), ("clip_init", _i),
+        ("max_iters", _i), ("clip_init", _i), ("preprocess", _i),
     ]
 
 

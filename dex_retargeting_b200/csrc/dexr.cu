@@ -41,6 +41,8 @@ struct SeqArgs {
   int steps;
   Dims dm;
   int scratch_off;
+  int spw;  // streams per warp: 32 / G when streams are plentiful; 1 when they are scarce (a stream is latency bound, and two
+            // streams sharing a warp both pay the larger of their two iteration counts on every frame)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -224,8 +226,10 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   constexpr int KPL = (3 * DEXR_NUM_KEYPOINTS + G - 1) / G;  // keypoint floats per lane
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int gid = warp * GPW + (lane / G);
-  const int groups_per_cta = NW * GPW;
+  const int gid = warp * GPW + (lane / G);               // scratch slot of this group of lanes
+  const int slot = a.spw == GPW ? gid : warp;            // which of the CTA's stream slots this group serves
+  const bool owner = a.spw == GPW || (lane / G) == 0;    // (scarce streams: only the first group of a warp carries one)
+  const int slots_per_cta = NW * a.spw;
   const uint32_t scratch_off = (uint32_t)(a.scratch_off + gid * (Scratch<G>::kFloats + 64) * 4);
   float* kpbuf = reinterpret_cast<float*>(smem + scratch_off) + Scratch<G>::kFloats;  // 63 floats: current keypoints
   Solver<G, BW> sv;
@@ -235,11 +239,11 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
 
   // Streams are dealt round-robin over CTAs (stream = blockIdx + gridDim * slot): with few streams every SM gets
   // one or two warps instead of a few SMs getting eight -- the path is latency bound per stream.
-  for (long long base = 0; base < a.S; base += (long long)gridDim.x * groups_per_cta) {
+  for (long long base = 0; base < a.S; base += (long long)gridDim.x * slots_per_cta) {
     // all groups of a warp must walk the time loop together (warp-wide shuffles inside solve)
-    const long long s = base + (long long)gid * gridDim.x + blockIdx.x;
-    const bool active = s < a.S;
-    const long long sc = active ? s : a.S - 1;
+    const long long s = base + (long long)slot * gridDim.x + blockIdx.x;
+    const bool active = owner && s < a.S;
+    const long long sc = (owner && s < a.S) ? s : a.S - 1;
     float last = 0.f, fy = 0.f;
     int finit = 0;
     if (active && sv.var >= 0) last = a.io.last_qpos[sc * a.dm.n_var + sv.var];
@@ -556,6 +560,7 @@ void dexr_default_params(dexr_params_t* p) {
   p->lambda0 = 1e-2f;
   p->max_iters = 64;
   p->clip_init = 0;
+  p->preprocess = 0;
 }
 
 int dexr_robot_create(const dexr_table_t* table_host, int device, dexr_robot_t** out) {
@@ -619,6 +624,7 @@ static int check_params(const dexr_params_t* p) {
   if (!(p->norm_delta >= 0.f)) return fail(DEXR_E_INVALID, "norm_delta must be >= 0");
   if (p->max_iters < 1 || p->max_iters > 65535) return fail(DEXR_E_INVALID, "max_iters out of range");
   if (!(p->tol > 0.f) || !(p->lambda0 > 0.f)) return fail(DEXR_E_INVALID, "tol and lambda0 must be > 0");
+  if (p->preprocess < 0 || p->preprocess > 2) return fail(DEXR_E_INVALID, "preprocess must be 0 (none), 1 (right hand) or 2 (left hand)");
   return 0;
 }
 
@@ -695,9 +701,10 @@ static int solver_kind(const dexr_table_t& t) {
   return (t.arrow > 0 && arrow_enabled()) ? 2 : 3;
 }
 
-static int check_frames_io(const dexr_table_t& t, const dexr_frames_t* io) {
+static int check_frames_io(const dexr_table_t& t, const dexr_frames_t* io, const dexr_params_t* prm) {
   if ((io->keypoints != nullptr) == (io->ref_value != nullptr))
     return fail(DEXR_E_INVALID, "exactly one of keypoints / ref_value must be given");
+  if (prm->preprocess != 0 && !io->keypoints) return fail(DEXR_E_INVALID, "preprocess needs raw keypoints, not ref_value");
   if (!io->last_qpos || !io->qpos_out) return fail(DEXR_E_INVALID, "last_qpos and qpos_out are required");
   if (t.n_fixed > 0 && !io->fixed_qpos) return fail(DEXR_E_INVALID, "robot has %d fixed joints but fixed_qpos is NULL", t.n_fixed);
   return 0;
@@ -718,7 +725,7 @@ extern "C" int dexr_solve_frames_multi(const dexr_group_t* groups, int32_t num_g
     if (g.num_frames == 0) continue;
     if (int e = check_params(g.params)) return e;
     dexr_robot* r = const_cast<dexr_robot*>(g.robot);
-    if (int e = check_frames_io(r->host, &g.io)) return e;
+    if (int e = check_frames_io(r->host, &g.io, g.params)) return e;
     if (device < 0) { device = r->device; sms = r->num_sms; first = r; }
     if (r->device != device) return fail(DEXR_E_INVALID, "group %d lives on device %d, group 0 on device %d: one launch, one device", i, r->device, device);
     const int k = solver_kind(r->host);
@@ -750,7 +757,7 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   if (num_frames == 0) return 0;
   if (int e = check_params(params)) return e;
   const dexr_table_t& t = robot->host;
-  if (int e = check_frames_io(t, io)) return e;
+  if (int e = check_frames_io(t, io, params)) return e;
   DEVICE_SCOPE(robot->device);
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
@@ -785,10 +792,16 @@ static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_
   const int smem = a.scratch_off + groups * (Scratch<G>::kFloats + 64) * 4;
   auto kern = dexr_sequences_kernel<G, BW, kSeqNW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  // spread streams over as many SMs as possible: latency bound, one stream per group
-  // one CTA per SM (up to 2 when there are many streams); fewer CTAs than SMs only when S is tiny
-  long long ctas = (S + GPW - 1) / GPW;  // at least one warp's worth of streams per CTA
-  int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * (S >= (long long)r->num_sms * groups * 2 ? 2 : 1));
+  // A stream is serial in time and latency bound, so streams are spread over as many warps and SMs as there are: while one
+  // warp per stream fits into one wave of CTAs (S <= SMs x warps per CTA), a warp carries ONE stream (the second group of a
+  // 16-lane solver idles); beyond that two 16-lane streams share a warp.  One CTA per SM, two when streams are plentiful.
+  const long long warps_one_wave = (long long)r->num_sms * kSeqNW;
+  a.spw = (GPW > 1 && S > warps_one_wave) ? GPW : 1;
+  static const int spw_env = [] { const char* e = getenv("DEXR_SEQ_PAIR"); return e ? atoi(e) : -1; }();  // A/B: 1 = always pair
+  if (spw_env == 1) a.spw = GPW;
+  const long long per_cta = (long long)kSeqNW * a.spw;
+  const long long ctas = std::max<long long>(1, (S + a.spw - 1) / a.spw);  // at least one warp's worth of streams per CTA
+  int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * (S >= (long long)r->num_sms * per_cta * 2 ? 2 : 1));
   kern<<<grid, kSeqNW * 32, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   {

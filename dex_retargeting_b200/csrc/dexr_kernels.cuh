@@ -480,6 +480,31 @@ struct Solver {
         const int ht = ST().res_ht[l], ho = ST().res_ho[l];
         tx = in.kp[3 * ht]; ty = in.kp[3 * ht + 1]; tz = in.kp[3 * ht + 2];
         if (ho >= 0) { tx -= in.kp[3 * ho]; ty -= in.kp[3 * ho + 1]; tz -= in.kp[3 * ho + 2]; }
+        if (prm.preprocess != 0) {
+          // Raw detector landmarks (single_hand_detector.py:100-103, 130-158): the map to wrist-centred MANO-convention
+          // points is p -> (p - wrist) . [x | n | z] . operator2mano, linear in p, so a vector target only needs the
+          // 3x3 part applied to the difference of its two landmarks and a position target to (landmark - wrist).
+          // Frame: n = plane normal of {wrist, index base (5), middle base (9)} (the reference takes it from an SVD: the
+          // same line up to sign), x = wrist - middle base made orthogonal to n, z = x x n, signs fixed so that z points
+          // from the middle base to the index base.  Every lane of the group computes it (uniform loads).
+          const float wx = in.kp[0], wy = in.kp[1], wz = in.kp[2];
+          if (ho < 0) { tx -= wx; ty -= wy; tz -= wz; }
+          const float ax = in.kp[15] - wx, ay = in.kp[16] - wy, az = in.kp[17] - wz;
+          const float bx = in.kp[27] - wx, by = in.kp[28] - wy, bz = in.kp[29] - wz;
+          float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz_ = ax * by - ay * bx;
+          const float nn = rsqrtf(nx * nx + ny * ny + nz_ * nz_);
+          nx *= nn; ny *= nn; nz_ *= nn;
+          float xx = -bx, xy = -by, xz = -bz;
+          const float dn = xx * nx + xy * ny + xz * nz_;
+          xx -= dn * nx; xy -= dn * ny; xz -= dn * nz_;
+          const float xn_ = rsqrtf(xx * xx + xy * xy + xz * xz);
+          xx *= xn_; xy *= xn_; xz *= xn_;
+          float zx = xy * nz_ - xz * ny, zy = xz * nx - xx * nz_, zz = xx * ny - xy * nx;
+          if (zx * (ax - bx) + zy * (ay - by) + zz * (az - bz) < 0.f) { nx = -nx; ny = -ny; nz_ = -nz_; zx = -zx; zy = -zy; zz = -zz; }
+          const float sgn = prm.preprocess == 2 ? -1.f : 1.f;  // operator2mano: right [[0,0,-1],[-1,0,0],[0,1,0]], left mirrors y
+          const float u = tx * xx + ty * xy + tz * xz, v = tx * nx + ty * ny + tz * nz_, w_ = tx * zx + ty * zy + tz * zz;
+          tx = -sgn * v; ty = sgn * w_; tz = -u;
+        }
       } else {
         tx = in.ref[3 * l]; ty = in.ref[3 * l + 1]; tz = in.ref[3 * l + 2];
       }

@@ -183,11 +183,19 @@ class Optimizer:
         self._device = device
         self._engine = _Engine(table, device, table_dev_ptr)
 
-    def params(self, clip_init: bool = False, lp_alpha: float = -1.0) -> N.DexrParams:
+    def params(self, clip_init: bool = False, lp_alpha: float = -1.0, raw_hand=None) -> N.DexrParams:
+        """`raw_hand`: None = the keypoints are wrist-centred MANO-convention points; HandType.right / left (or "right" /
+        "left") = they are RAW detector landmarks of that hand and the kernel pre-processes them itself (fused
+        single_hand_detector.py:100-103, 130-158)."""
         p = N.default_params()
         p.tol, p.lambda0, p.max_iters = self.step_tol, self.lambda0, int(self.max_iters)
         p.clip_init = 1 if clip_init else 0
         p.lp_alpha = float(lp_alpha)
+        if raw_hand is not None:
+            name = raw_hand if isinstance(raw_hand, str) else raw_hand.name
+            if name not in ("right", "left"):
+                raise ValueError(f"raw_hand must be right or left, got {raw_hand!r}")
+            p.preprocess = 1 if name == "right" else 2
         self._loss_params(p)
         return p
 
@@ -242,7 +250,7 @@ class Optimizer:
         return qpos, rq
 
     def retarget_batch_host(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
-                            out=None, clip_init=False):
+                            out=None, clip_init=False, raw_hand=None):
         """Host-buffer twin of `retarget_batch`: float32 numpy arrays (or CPU torch tensors, ideally
         pinned) in, numpy out.  The library stages chunks through its own device buffers and overlaps the
         host->device copies, the solve and the device->host copies (`dexr_solve_frames_host`).  Returns
@@ -291,30 +299,32 @@ class Optimizer:
         if out_np.dtype != np.float32 or not out_np.flags.c_contiguous:
             raise ValueError("out must be a contiguous float32 array")
         io.qpos_out = ptr(out_np, (B, self.opt_dof), "out")
-        p = self.params(clip_init=clip_init)
+        p = self.params(clip_init=clip_init, raw_hand=raw_hand)
         N.check(eng.lib.dexr_solve_frames_host(eng.handle, C.byref(p), C.byref(io), B), "dexr_solve_frames_host")
         return out
 
     # ---------------------------------------------------------------- device path (torch, B large)
     def retarget_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
-                       out=None, robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None):
+                       out=None, robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None, raw_hand=None):
         """Solve B independent frames in one launch.  All arguments are float32 CUDA tensors on this
         optimizer's device (projected: uint8, status_out: int32), contiguous:
           ref_value [B,m,3]  OR  keypoints [B,21,3] (the human-index gather is done in the kernel)
           fixed_qpos [B,len(idx_pin2fixed)] (omit when there are none), last_qpos [B,opt_dof]
+        `raw_hand` (HandType): `keypoints` are raw detector landmarks of that hand; the wrist-frame estimate and the MANO
+        rotation of the reference's detector are applied inside the solver (see `params`).
         Returns qpos [B,opt_dof] (= `out` if given).  Nothing is synchronised."""
         import torch
 
         eng, io, p, out, B = self._prepare_batch(ref_value, fixed_qpos, last_qpos, keypoints=keypoints, projected=projected, out=out,
                                                  robot_qpos_out=robot_qpos_out, status_out=status_out, cost_out=cost_out,
-                                                 clip_init=clip_init)
+                                                 clip_init=clip_init, raw_hand=raw_hand)
         s = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", eng.device))
         N.check(eng.lib.dexr_solve_frames(eng.handle, C.byref(p), C.byref(io), B, C.c_void_p(s.cuda_stream)),
                 "dexr_solve_frames")
         return out
 
     def _prepare_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None, out=None,
-                       robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False):
+                       robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, raw_hand=None, stream=None):
         """Validate the tensors of one batch and lay them out as `dexr_frames_t` (shared by the single-robot and the
         mixed-robot launch).  Returns (engine, io, params, out, B)."""
         import torch
@@ -356,7 +366,9 @@ class Optimizer:
             io.cost_out = chk(cost_out, (B,), torch.float32, "cost_out")
         if projected is not None:
             io.projected = chk(projected, (B, self._objective_spec().len_proj), torch.uint8, "projected")
-        return eng, io, self.params(clip_init=clip_init), out, B
+        if raw_hand is not None and keypoints is None:
+            raise ValueError("raw_hand needs `keypoints` (raw landmarks), not ref_value")
+        return eng, io, self.params(clip_init=clip_init, raw_hand=raw_hand), out, B
 
 
 def retarget_batch_mixed(jobs, stream=None):

@@ -215,11 +215,12 @@ class SeqRetargeting:
         )
 
     def retarget_sequences(self, keypoints, state: Optional[StreamState] = None, fixed_qpos=None, out=None,
-                           status_out=None, stream=None):
+                           status_out=None, stream=None, raw_hand=None):
         """keypoints: float32 CUDA tensor [S,T,21,3] (raw 21-point hand frames).  Runs every stream
         through T SeqRetargeting.retarget() steps in one launch.  Returns (robot_qpos [S,T,dof] float32
         in pinocchio joint order, filtered; state) -- `state` is updated in place and can be passed
-        to the next call to continue the streams."""
+        to the next call to continue the streams.  `raw_hand` (HandType): the keypoints are raw detector landmarks of that
+        hand, pre-processed inside the kernel (Optimizer.params)."""
         import torch
 
         opt = self.optimizer
@@ -255,7 +256,7 @@ class SeqRetargeting:
         if status_out is not None:
             io.status_out = chk(status_out, (S, T), torch.int32, "status_out")
         s = stream if stream is not None else torch.cuda.current_stream(dev)
-        p = opt.params(clip_init=True, lp_alpha=self.low_pass_alpha)
+        p = opt.params(clip_init=True, lp_alpha=self.low_pass_alpha, raw_hand=raw_hand)
         N.check(eng.lib.dexr_solve_sequences(eng.handle, C.byref(p), C.byref(io), S, T, C.c_void_p(s.cuda_stream)),
                 "dexr_solve_sequences")
         return out, state

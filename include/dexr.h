@@ -144,6 +144,13 @@ typedef struct dexr_params {
   float lambda0;      /* initial LM damping; default 1e-2 */
   int32_t max_iters;  /* cap on accepted iterations; default 64 */
   int32_t clip_init;  /* 1: clip the warm start to clip_lo/clip_hi first (SeqRetargeting.retarget) */
+  int32_t preprocess; /* keypoints mode only.  0: `keypoints` are wrist-centred MANO-convention points (what the reference's
+                       * detector hands to the retargeting).  1 (right hand) / 2 (left hand): `keypoints` are RAW detector
+                       * landmarks and the solver prelude applies example/vector_retargeting/single_hand_detector.py:100-103,
+                       * 130-158 itself -- wrist frame from landmarks {0,5,9}, rotation into it and into the MANO convention
+                       * (constants.py:7-21) -- to the few keypoints the objective reads: no separate launch, no second
+                       * 252 B / frame round trip through HBM (dexr_preprocess_keypoints remains for callers that want the
+                       * transformed frames themselves) */
 } dexr_params_t;
 
 /* Buffers of one batched solve.  All pointers are DEVICE pointers (or NULL where noted); rows are

@@ -36,13 +36,13 @@ def load(defines: tuple = ()):
 
 
 def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None, projected=None, defines=(), use_arrow=True,
-                 clip_init=False, want_robot_qpos=False):
+                 clip_init=False, want_robot_qpos=False, raw_hand=None):
     """Emulated dexr_solve_frames for an Optimizer of the host mirror.  Returns (qpos [B,n], status [B], cost [B])
     (+ the full joint vector [B,dof] with want_robot_qpos)."""
     from dex_retargeting_b200 import _native as N
 
     lib = load(tuple(defines))
-    table, prm = opt.build_table(), opt.params(clip_init=clip_init)
+    table, prm = opt.build_table(), opt.params(clip_init=clip_init, raw_hand=raw_hand)
     B, n = last_qpos.shape[0], table.n_var
 
     def f32(a):
@@ -66,14 +66,14 @@ def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None
     return (out, status, cost, full) if want_robot_qpos else (out, status, cost)
 
 
-def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True):
+def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_hand=None):
     """Emulated dexr_solve_sequences for a SeqRetargeting of the host mirror: keypoints [S,T,21,3] -> filtered robot qpos
     [S,T,dof]; `state` = dict(last_qpos, filter_state, filter_init, projected) carried between calls (created if None)."""
     from dex_retargeting_b200 import _native as N
 
     lib = load(tuple(defines))
     opt = seq.optimizer
-    table, prm = opt.build_table(), opt.params(clip_init=True, lp_alpha=seq.low_pass_alpha)
+    table, prm = opt.build_table(), opt.params(clip_init=True, lp_alpha=seq.low_pass_alpha, raw_hand=raw_hand)
     kp = np.ascontiguousarray(keypoints, dtype=np.float32)
     S, T = kp.shape[:2]
     assert table.n_fixed == 0, "streams with fixed joints: not wired in the emulation helper"

@@ -85,3 +85,75 @@ def test_preprocess_argument_checks():
     out = preprocess_keypoints(bad)
     torch.cuda.synchronize()
     assert torch.isnan(out[:, 1:]).all()
+
+
+@pytest.mark.parametrize("key,hand", [("teleop/allegro_hand_right", "right"), ("teleop/leap_hand_right_dexpilot", "right"),
+                                      ("teleop/shadow_hand_left", "left"), ("offline/allegro_hand_left", "left")])
+def test_fused_preprocessing_equals_separate_launch_and_oracle(key, hand):
+    """raw landmarks -> qpos in ONE launch (`raw_hand=`: the solver prelude does the detector post-processing,
+    dexr_params_t.preprocess) against (a) the two-launch path preprocess_keypoints -> retarget_batch and (b) the oracle:
+    oracle/preprocess.py (the reference's SVD frame estimate, float64) followed by the converged float64 solve."""
+    from helpers import build_oracle, build_product
+    from dex_retargeting_b200.constants import HandType
+    from dex_retargeting_b200.preprocess import preprocess_keypoints
+    from oracle.solvers import solve_converged
+
+    seq, o = build_product(key, device=0), build_oracle(key)
+    opt = seq.optimizer
+    rng = np.random.RandomState(3)
+    base = keypoint_trajectory()[::5][:96].astype(np.float64)
+    if hand == "left":
+        base = base * np.array([-1.0, 1.0, 1.0])
+    B = base.shape[0]
+    raw = (np.einsum("bij,bkj->bki", random_rotations(B, rng), base) + rng.randn(B, 1, 3) * 0.3).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    x0 = torch.from_numpy(np.tile(seq.joint_limits.mean(1).astype(np.float32), (B, 1))).to(dev)
+    nf = len(opt.idx_pin2fixed)
+    fixed = torch.zeros((B, nf), dtype=torch.float32, device=dev) if nf else None
+
+    def proj():
+        return torch.zeros((B, opt._objective_spec().len_proj), dtype=torch.uint8, device=dev) if opt.retargeting_type == "DEXPILOT" else None
+
+    traw = torch.from_numpy(raw).to(dev)
+    st = torch.zeros((B,), dtype=torch.int32, device=dev)
+    p_f = proj()
+    q_fused = opt.retarget_batch(keypoints=traw, last_qpos=x0, fixed_qpos=fixed, projected=p_f, status_out=st, raw_hand=HandType[hand])
+    p_s = proj()
+    q_sep = opt.retarget_batch(keypoints=preprocess_keypoints(traw, HandType[hand]), last_qpos=x0, fixed_qpos=fixed, projected=p_s)
+    torch.cuda.synchronize()
+    assert int((st >> 24).max()) == 0
+    if p_f is not None:
+        assert torch.equal(p_f, p_s)
+    d = (q_fused - q_sep).abs().amax(1).cpu().numpy()
+    assert np.median(d) < 2e-6 and (d < 1e-4).mean() >= 0.97, (np.median(d), d.max())  # same map, other rounding order
+    qf = q_fused.cpu().numpy()
+    inside = 0
+    for b in range(0, B, 4):
+        kp, _ = preprocess(raw[b], hand)
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        xb = solve_converged(o, o.ref_from_keypoints(kp.astype(np.float32)), np.zeros(nf), x0[b].cpu().numpy(), update_state=False)[0]
+        inside += np.abs(qf[b] - xb).max() < 1e-4
+    assert inside >= (B // 4) - 2, inside
+
+
+def test_fused_preprocessing_in_streams():
+    """Streams of RAW landmarks: retarget_sequences(raw, raw_hand=...) equals retarget_sequences(preprocess_keypoints(raw))."""
+    from helpers import build_product
+    from dex_retargeting_b200.constants import HandType
+    from dex_retargeting_b200.preprocess import preprocess_keypoints
+
+    seq = build_product("teleop/leap_hand_right_dexpilot", device=0)
+    rng = np.random.RandomState(4)
+    base = keypoint_trajectory()[:80].astype(np.float64)
+    S = 6
+    R, t = random_rotations(S, rng), rng.randn(S, 1, 1, 3) * 0.3
+    raw = (np.einsum("sij,tkj->stki", R, base) + t).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    traw = torch.from_numpy(np.ascontiguousarray(raw)).to(dev)
+    a, sa = seq.retarget_sequences(traw, raw_hand=HandType.right)
+    b, sb = seq.retarget_sequences(preprocess_keypoints(traw, HandType.right))
+    torch.cuda.synchronize()
+    assert torch.equal(sa.projected, sb.projected)
+    d = (a - b).abs().amax(2).cpu().numpy()
+    assert np.median(d) < 2e-6 and (d < 1e-4).mean() > 0.9, (np.median(d), d.max())

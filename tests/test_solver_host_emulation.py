@@ -221,3 +221,42 @@ def test_out_of_reach_targets_do_not_cycle():
     refs = (refs * 1.25).astype(np.float32)
     q, st, _ = emu_host.solve_frames(seq.optimizer, x0, ref_value=refs)
     assert np.all((st >> 24) == 0), st >> 23
+
+
+@pytest.mark.parametrize("key,hand", [("teleop/allegro_hand_right", "right"), ("teleop/leap_hand_right_dexpilot", "right"),
+                                      ("teleop/shadow_hand_left", "left"), ("offline/leap_hand_left", "left")])
+def test_fused_keypoint_preprocessing_matches_detector_oracle(key, hand):
+    """`dexr_params_t.preprocess`: raw detector landmarks (recorded hand frames under random camera poses) go straight into
+    the solver, which applies single_hand_detector.py:100-103, 130-158 in its prelude.  Against oracle/preprocess.py (the
+    reference's SVD-based frame estimate, float64) followed by the oracle's converged solve, vector, DexPilot and position
+    targets, both hands."""
+    from oracle.preprocess import preprocess
+    from oracle.solvers import solve_converged
+
+    seq, o = build_product(key), build_oracle(key)
+    rng = np.random.RandomState(12)
+    base = keypoint_trajectory()[::23][:12].astype(np.float64)
+    if hand == "left":
+        base = base * np.array([-1.0, 1.0, 1.0])  # mirror the recorded right hand
+    B = base.shape[0]
+    q4 = rng.randn(B, 4)
+    q4 /= np.linalg.norm(q4, axis=1, keepdims=True)
+    w, x, y, z = q4.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                  np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                  np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
+    raw = (np.einsum("bij,bkj->bki", R, base) + rng.randn(B, 1, 3) * 0.3).astype(np.float32)
+    x0 = np.tile(seq.joint_limits.mean(1).astype(np.float32), (B, 1))
+    nf = len(seq.optimizer.idx_pin2fixed)
+    fixed = np.zeros((B, nf), np.float32) if nf else None
+    proj = np.zeros((B, len(o.projected)), np.uint8) if o.type == "dexpilot" else None
+    q, st, _ = emu_host.solve_frames(seq.optimizer, x0, keypoints=raw, fixed_qpos=fixed, projected=proj, raw_hand=hand)
+    assert np.all((st >> 24) == 0)
+    inside = 0
+    for b in range(B):
+        kp, _ = preprocess(raw[b], hand)
+        if o.type == "dexpilot":
+            o.projected[:] = False
+        xb = solve_converged(o, o.ref_from_keypoints(kp.astype(np.float32)), np.zeros(nf), x0[b], update_state=False)[0]
+        inside += np.abs(q[b] - xb).max() < TOL
+    assert inside >= B - 2, inside  # mid-range cold start on recorded frames: an occasional other basin
