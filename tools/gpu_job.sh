@@ -36,3 +36,37 @@ if want dumpvar; then
   DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_pdfallback_fknoise.so python tests/tools/dump_status.py "$out/status_pdfallback_fknoise.npz" 2>&1 | tee "$out/dump_pdfallback_fknoise.log"
   DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_fknoise.so python tests/tools/dump_status.py "$out/status_fknoise.npz" 2>&1 | tee "$out/dump_fknoise.log"
 fi
+if want mixedab; then
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_default.json" 2> "$out/bench_default.err"
+  DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_multi_calls.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_multi_calls.json" 2> "$out/bench_multi_calls.err"
+  DEXR_SEQ_PAIR=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_seq_pair.json" 2> "$out/bench_seq_pair.err"
+  python - <<'PY'
+import json
+for n in ("default", "multi_calls", "seq_pair"):
+    try:
+        d = json.loads(open(f"gpurun_out/job/bench_{n}.json").read().strip().splitlines()[-1])
+        c = {r["name"]: r for r in d["configs"]}
+        print(f"{n:12s} headline {d['value']:.4e}  mixed {c['mixed_robots']['ms_per_step']:.3f} ms (six launches {c['mixed_robots'].get('six_launches_ms_this_rank', 0):.3f})  streams {c['leap_dexpilot_streams']['ms_per_step']:.3f} ms")
+    except Exception as e:
+        print(n, "FAILED", e)
+PY
+fi
+if want streams256; then
+  python - <<'PY'
+import sys, torch
+sys.path.insert(0, "tools")
+import workloads as W
+dev = torch.device("cuda", 0)
+seq = W.build(W.LEAP_DEXPILOT_KEY, device=0)
+for S in (64, 256, 1024, 2048, 4096):
+    tk = torch.from_numpy(W.streams(max(S, 2048), 300)[:S] if S <= 2048 else __import__("numpy").concatenate([W.streams(2048, 300)] * 2)).to(dev)
+    seq.retarget_sequences(tk)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        seq.retarget_sequences(tk)
+    e1.record(); torch.cuda.synchronize()
+    print(f"streams {S:5d} x 300: {e0.elapsed_time(e1) / 3:.3f} ms  launch {seq.optimizer.engine().launch_info()}")
+PY
+fi
