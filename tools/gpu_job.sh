@@ -70,3 +70,6 @@ for S in (64, 256, 1024, 2048, 4096):
     print(f"streams {S:5d} x 300: {e0.elapsed_time(e1) / 3:.3f} ms  launch {seq.optimizer.engine().launch_info()}")
 PY
 fi
+if want multisweep; then
+  python tools/multi_sweep.py 2>&1 | tee "$out/multi_sweep.txt"
+fi
