@@ -739,17 +739,17 @@ extern "C" int dexr_solve_frames_multi(const dexr_group_t* groups, int32_t num_g
   if (m.n_groups == 0) return 0;
   DEVICE_SCOPE(device);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  // Two ways to run the groups, chosen by size (DEXR_MULTI_MODE=persistent|streams forces one):
-  //  * persistent: ONE launch, every CTA walks the groups (dexr_frames_multi_kernel).  No launch per robot and a single
-  //    tail, but the four solver bodies share one register allocation (B200: 3.9 ms against 3.1 ms for six robots x 16 384
-  //    frames) -- the choice when the groups are small and the launches themselves are what costs;
-  //  * streams: one standalone launch per group on library-owned side streams forked from and joined back into the
-  //    caller's stream with events, so the kernels overlap each other's tails -- the choice for large groups.
-  static const int mode_env = [] {
-    const char* e = getenv("DEXR_MULTI_MODE");
-    return !e ? 0 : (!strcmp(e, "persistent") ? 1 : (!strcmp(e, "streams") ? 2 : 0));
-  }();
-  const bool persistent = mode_env == 1 || (mode_env == 0 && tiles <= 2LL * sms);
+  // Two ways to run the groups:
+  //  * streams (default): one standalone launch per group on library-owned side streams, forked from and joined back into
+  //    the caller's stream with events.  Small groups have small grids and run side by side on different SMs, large ones
+  //    overlap each other's tails.
+  //  * persistent (DEXR_MULTI_MODE=persistent, read per call): ONE launch whose CTAs walk the groups
+  //    (dexr_frames_multi_kernel).  Built as VERDICT r01 proposed and measured on B200 against the above -- six robots x n
+  //    frames: n = 64: 0.36 vs 0.22 ms, 1024: 0.83 vs 0.61, 16 384: 3.85 vs 3.13 (one launch after the other: 0.69 / 0.83 /
+  //    3.59): the four solver bodies share one register allocation (708 B of spills against 124 B), and a CTA runs its
+  //    groups one after the other where separate small grids run concurrently.  Kept for A/B runs; not the default.
+  const char* mode_env = getenv("DEXR_MULTI_MODE");
+  const bool persistent = mode_env && !strcmp(mode_env, "persistent");
   if (persistent) {
     auto kern = dexr_frames_multi_kernel<NCW>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

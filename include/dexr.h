@@ -213,9 +213,10 @@ int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t* params, co
 /* Mixed robots: several (robot, batch) groups solved by ONE persistent launch -- replaces one Optimizer per robot run one
  * after the other (retargeting_config.py:167-257 builds exactly one optimizer per config).  Every group has its own table,
  * parameters and buffers (all on the same device); results are bit-identical to one dexr_solve_frames call per group.
- * Small groups (at most two tiles per SM in total) run inside one persistent kernel whose CTAs walk the groups; large groups
- * run as one launch per group on library-owned side streams forked from / joined into `cuda_stream` with events.  Either way
- * the call is asynchronous and ordered on `cuda_stream`. */
+ * The groups run as one launch each on library-owned side streams forked from / joined into `cuda_stream` with events (small
+ * grids side by side, large ones overlapping their tails); DEXR_MULTI_MODE=persistent selects the single persistent kernel
+ * whose CTAs walk the groups instead (measured slower on B200, see csrc/dexr.cu).  Either way the call is asynchronous and
+ * ordered on `cuda_stream`. */
 typedef struct dexr_group {
   const dexr_robot_t* robot;
   const dexr_params_t* params;

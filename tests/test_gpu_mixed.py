@@ -44,8 +44,13 @@ def _clone(kw):
      [500, 300, 200, 4096, 50]),                                                        # dexpilot flags, free-flying bases, prismatic
     ([W.METRIC_KEY], [5000]),                                                           # a single group
 ], ids=["six-robots", "ragged", "loss-families", "single"])
-def test_mixed_launch_equals_per_robot_launches(keys, sizes):
+@pytest.mark.parametrize("mode", ["streams", "persistent"])
+def test_mixed_launch_equals_per_robot_launches(keys, sizes, mode, monkeypatch):
+    """Both implementations behind dexr_solve_frames_multi: fork-join launches on side streams (default) and the single
+    persistent kernel whose CTAs walk the groups (DEXR_MULTI_MODE=persistent, read per call)."""
     import torch
+
+    monkeypatch.setenv("DEXR_MULTI_MODE", mode)
 
     from dex_retargeting_b200.optimizer import retarget_batch_mixed
 
