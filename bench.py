@@ -443,6 +443,9 @@ def main():
                           note="dummy joints drawn from " + ("+-0.5 m / +-pi" if narrow else "the shipped +-5 m / +-2 pi"))
         # config 4: DexPilot LEAP, 2048 streams x 300 frames in total, streams split over the ranks
         lp = W.build(W.LEAP_DEXPILOT_KEY, device=local_rank)
+        kd, xd, _, _ = W.frames(lp, FRAMES_PER_GPU, W.SHADOW_SEED)
+        frames_record("leap_dexpilot_frames", "config-4-arm", lp, [(kd, xd, None)], FRAMES_PER_GPU, "weak", tag="leap_frames", reps=5,
+                      note="the config-4 objective on independent frames (hysteresis flags start cleared)")
         S, T = 2048, 300
         kps = W.streams(S, T)
         b, e = shard_range(S, rank, world)
@@ -539,7 +542,7 @@ def main():
             tj = tj if "captures" in tj else {"captures": {"metric": tj}}
             for name, c in tj["captures"].items():
                 if c.get("build_id") == build_id:
-                    captures[name] = c
+                    captures[(name.split("@")[0], c.get("frames_per_launch"))] = c
             if not captures:
                 cap_note = f"profiles/roofline_traffic.json was captured from another library build (loaded build {build_id}): traffic / issue / fp32 withheld"
 
@@ -547,8 +550,8 @@ def main():
             ach = bpf * frames_per_launch / (ms * 1e-3) / 1e9
             r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                  "peak_source": peak_src, "bytes_per_frame": bpf, "launch_ms": ms}
-            c = captures.get(name)
-            if c and c.get("frames_per_launch") == frames_per_launch:
+            c = captures.get((name, frames_per_launch))
+            if c:
                 r["traffic"] = c.get("dram_bytes_per_launch")
                 if c.get("warp_inst_per_launch"):
                     a = c["warp_inst_per_launch"] / (ms * 1e-3)

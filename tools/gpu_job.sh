@@ -73,3 +73,22 @@ fi
 if want multisweep; then
   python tools/multi_sweep.py 2>&1 | tee "$out/multi_sweep.txt"
 fi
+if want final; then
+  # the record run: captures first, then the traffic file of THIS build, then the bench line that reads it
+  BID=$(python -c "from dex_retargeting_b200 import _native as N; print(N.build_id())")
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file "$out/launches_bench.csv" \
+      python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/ncu_launches.log" 2>&1
+  ncu --set full --metrics "$M" --clock-control none --import-source on -k regex:dexr_frames_kernel -s 4 -c 1 -f -o "$out/prof_frames_allegro" \
+      python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs > "$out/ncu_full.log" 2>&1
+  ncu --set full --metrics "$M" --clock-control none --import-source on -k regex:dexr_ -s 1 -c 1 -f -o "$out/prof_frames_shadowpos" python tools/profile_targets.py shadow > "$out/ncu_shadow.log" 2>&1
+  ncu --set full --metrics "$M" --clock-control none --import-source on -k regex:dexr_ -s 1 -c 1 -f -o "$out/prof_frames_leapdp" python tools/profile_targets.py leapdp > "$out/ncu_leapdp.log" 2>&1
+  ncu --set full --metrics "$M" --clock-control none --import-source on -k regex:dexr_ -s 1 -c 1 -f -o "$out/prof_streams_256x300" python tools/profile_targets.py streams > "$out/ncu_streams.log" 2>&1
+  ncu --set full --metrics "$M" --clock-control none --import-source on -k regex:dexr_ -s 1 -c 1 -f -o "$out/prof_streams_2048x300" python tools/profile_targets.py streams2048 > "$out/ncu_streams2048.log" 2>&1
+  python tools/make_traffic.py "$out" profiles/roofline_traffic.json "$BID" && cp profiles/roofline_traffic.json "$out/roofline_traffic.json"
+  nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > "$out/clocks.csv" &
+  SMI=$!
+  python bench.py > "$out/bench.json" 2> "$out/bench.err"; echo "bench exit $?"
+  python bench.py --impl reference > "$out/bench_reference.json" 2> "$out/bench_reference.err"; echo "reference arm exit $?"
+  kill $SMI
+  du -sh "$out"
+fi

@@ -12,7 +12,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tools"))
 import workloads as W  # noqa: E402
 
-which = sys.argv[1:] or ["shadow", "leapdp", "streams"]
+which = sys.argv[1:] or ["shadow", "leapdp", "streams", "streams2048"]
 dev = torch.device("cuda", 0)
 if "shadow" in which:
     seq = W.build(W.SHADOW_POS_KEY, device=0)
@@ -28,7 +28,13 @@ if "leapdp" in which:
     torch.cuda.synchronize()
 if "streams" in which:
     seq = W.build(W.LEAP_DEXPILOT_KEY, device=0)
-    for S, T in ((256, 300), (2048, 60)):
-        seq.retarget_sequences(torch.from_numpy(W.streams(S, T)).to(dev))
-        seq.retarget_sequences(torch.from_numpy(W.streams(S, T)).to(dev))
+    tk = torch.from_numpy(W.streams(2048, 300)[:256]).to(dev)
+    seq.retarget_sequences(tk)
+    seq.retarget_sequences(tk)
+    torch.cuda.synchronize()
+if "streams2048" in which:
+    seq = W.build(W.LEAP_DEXPILOT_KEY, device=0)
+    tk = torch.from_numpy(W.streams(2048, 300)).to(dev)
+    seq.retarget_sequences(tk)
+    seq.retarget_sequences(tk)
     torch.cuda.synchronize()
