@@ -119,6 +119,21 @@ __device__ __forceinline__ unsigned gballot(bool p, int lane) {
   return (b >> (lane & ~(G - 1))) & ((1u << (G & 31)) - 1u);
 }
 
+template <int N>
+struct ChunkTag { static constexpr int value = N; };
+
+// 1 / sqrt(x) for x >= 1e-20 (no denormals, no zero): the bare MUFU.RSQ (rsqrt.approx.ftz, 2^-22 relative) -- rsqrtf() wraps it
+// in a denormal rescue of four more instructions, once per Cholesky pivot
+__device__ __forceinline__ float fast_rsqrt(float x) {
+#ifndef DEXR_HOST_EMULATION
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
 __device__ __forceinline__ float huber_val(float d, float beta, float inv_beta) {
   return d < beta ? 0.5f * d * d * inv_beta : d - 0.5f * beta;
 }
@@ -1028,31 +1043,52 @@ struct Solver {
             }
           }
         }
-        for (int k = 0; k < (AR ? 0 : bw); ++k) {
-          const int pk = cb + k;  // pivot lane (of this lane's block)
-          float hk = H[0];
-          if (pk == l) hk += fmaf(lam, D, reg2);
-          const float dkk = gshfl<G>(hk, pk);
-          bad = bad || !(dkk > 1e-20f);
-          const float inv = rsqrtf(fmaxf(dkk, 1e-20f));
-          const float lik = hk * inv;                       // L[l][k] (meaningful for l >= k)
-          const float yk = gshfl<G>(y, pk) * inv;           // forward substitution fused
-          if (l == pk) { myinv = inv; y = yk; }
-          if (l > pk) y = fmaf(-lik, yk, y);
-          float* row = Lr + (k & 1) * NP + cb;
-          row[(l - pk - 1) & (dense ? NP - 1 : BW - 1)] = lik;  // entry j of the row = L[pk+1+j][pk]
-          Lc[k * (NP + 1) + l] = lik;                       // transposed copy for the back substitution
-          __syncwarp();
-          const int live = bw - k - 1;                      // columns right of the pivot (inside the block)
+        if constexpr (!AR) {
+          // One pivot step, with the number of 4-column chunks of the rotating window it updates fixed at compile time.  The
+          // window shrinks by one column per pivot, so the steps are run in PHASES of decreasing chunk count (HN = 16: 4, 3,
+          // 2, 1 chunks while more than 12, 8, 4, 0 columns are live) instead of predicating all HN / 4 chunks off one by
+          // one: half of the FFMA / LDS.128 issue slots of a 16 x 16 factorisation went into predicated-off instructions.
+          constexpr int kMask = dense ? NP - 1 : BW - 1;
+          const float shift = fmaf(lam, D, reg2);               // damping + regulariser, added to the pivot at pivot time
+          int k = 0;
+          auto pivot_steps = [&](auto chunks_tag, int stop_live) {
+            constexpr int NC = decltype(chunks_tag)::value;
+            for (; k < bw && bw - k - 1 > stop_live; ++k) {
+              const int pk = cb + k;  // pivot lane (of this lane's block)
+              float hk = H[0];
+              if (pk == l) hk += shift;
+              const float dkk = gshfl<G>(hk, pk);
+              bad = bad || !(dkk > 1e-20f);
+              const float inv = fast_rsqrt(fmaxf(dkk, 1e-20f));
+              const float lik = hk * inv;                       // L[l][k] (meaningful for l >= k)
+              const float yk = gshfl<G>(y, pk) * inv;           // forward substitution fused
+              if (l == pk) { myinv = inv; y = yk; }
+              if (l > pk) y = fmaf(-lik, yk, y);
+              float* row = Lr + (k & 1) * NP + cb;              // two NP-float row buffers, alternating per pivot
+              row[(l - pk - 1) & kMask] = lik;                  // entry j of the row = L[pk+1+j][pk]
+              Lc[k * (NP + 1) + l] = lik;                       // transposed copy for the back substitution
+              __syncwarp();
+              const int live = bw - k - 1;                      // columns right of the pivot (inside the block)
 #pragma unroll
-          for (int j = 0; j < HN; j += 4) {
-            if (j < live) {
-              const float4 r = *reinterpret_cast<const float4*>(row + j);
-              H[j + 0] = fmaf(-lik, r.x, H[j + 1]);
-              if (j + 2 < HN) H[j + 1] = fmaf(-lik, r.y, H[j + 2]);
-              if (j + 3 < HN) H[j + 2] = fmaf(-lik, r.z, H[j + 3]);
-              if (j + 4 < HN) H[j + 3] = fmaf(-lik, r.w, H[j + 4]);
+              for (int j = 0; j < 4 * NC; j += 4) {
+                if (j + 4 < 4 * NC || j < live) {               // (only the last chunk of a phase can be entirely dead)
+                  const float4 r = *reinterpret_cast<const float4*>(row + j);
+                  H[j + 0] = fmaf(-lik, r.x, H[j + 1]);
+                  if (j + 2 < HN) H[j + 1] = fmaf(-lik, r.y, H[j + 2]);
+                  if (j + 3 < HN) H[j + 2] = fmaf(-lik, r.z, H[j + 3]);
+                  if (j + 4 < HN) H[j + 3] = fmaf(-lik, r.w, H[j + 4]);
+                }
+              }
             }
+          };
+          if constexpr (HN == 32) {
+            pivot_steps(ChunkTag<8>{}, 24); pivot_steps(ChunkTag<6>{}, 16); pivot_steps(ChunkTag<4>{}, 8); pivot_steps(ChunkTag<2>{}, -1);
+          } else if constexpr (HN == 16) {
+            pivot_steps(ChunkTag<4>{}, 12); pivot_steps(ChunkTag<3>{}, 8); pivot_steps(ChunkTag<2>{}, 4); pivot_steps(ChunkTag<1>{}, -1);
+          } else if constexpr (HN == 8) {
+            pivot_steps(ChunkTag<2>{}, 4); pivot_steps(ChunkTag<1>{}, -1);
+          } else {
+            pivot_steps(ChunkTag<HN / 4>{}, -1);
           }
         }
         // back substitution: L^T delta = y (column oriented, transposed copy read conflict free)

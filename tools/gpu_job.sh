@@ -92,3 +92,19 @@ if want final; then
   kill $SMI
   du -sh "$out"
 fi
+if want abprev; then
+  for n in default prev; do
+    if [ $n = prev ]; then export DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_prev.so; else unset DEXR_LIBRARY; fi
+    python bench.py --steps 20 --warmup 3 --no-cpu-baseline > "$out/bench_$n.json" 2> "$out/bench_$n.err"
+  done
+  unset DEXR_LIBRARY
+  python - <<'PY'
+import json
+for n in ("default", "prev"):
+    try:
+        d = json.loads(open(f"gpurun_out/job/bench_{n}.json").read().strip().splitlines()[-1])
+        print(f"{n:8s} headline {d['value']:.4e} sustained {d['sustained']['value']:.4e} | " + " | ".join(f"{r['name'][:22]} {r['ms_per_step']:.4f}" for r in d["configs"]))
+    except Exception as e:
+        print(n, "FAILED", e)
+PY
+fi
