@@ -77,7 +77,7 @@ def main():
                 return None
             v = float(data[0][col[k]].replace(",", ""))
             u = units[col[k]]
-            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(u, 1)
             return v * mult * scale
 
         rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
