@@ -287,8 +287,8 @@ struct Scratch {
   static constexpr int NP = G;
   static constexpr int kFr = 0;                                 // [MAX_RES][4] target xyz, weight c_k
   static constexpr int kLp = kFr + DEXR_MAX_RES * 4;            // [2][MAX_LINKS][4] link positions
-  static constexpr int kU = kLp + 2 * DEXR_MAX_LINKS * 4;       // jbuf[2][3][NP] (aliased by the 2 Cholesky row buffers) + at[NP][8]
-  static constexpr int kUSize = 14 * NP;
+  static constexpr int kU = kLp + 2 * DEXR_MAX_LINKS * 4;       // jbuf[2][3][NP] (aliased by the 2 Cholesky row buffers) + at: 2 x [NP + NP/4] float4
+  static constexpr int kUSize = 16 * NP;
   static constexpr int kHb = kU + kUSize;                       // [NP][NP]   Hessian backup, column per lane
   static constexpr int kLcol = kHb + NP * NP;                   // [NP][NP+1] L^T rows, conflict-free column reads (also mimic-fold temp)
   static constexpr int kFloats = ((kLcol + NP * (NP + 1) + 3) / 4) * 4;
@@ -360,7 +360,12 @@ struct Solver {
   __device__ __forceinline__ float4* fr() const { return reinterpret_cast<float4*>(scf() + SC::kFr); }
   __device__ __forceinline__ float4* lp(int b) const { return reinterpret_cast<float4*>(scf() + SC::kLp) + b * DEXR_MAX_LINKS; }
   __device__ __forceinline__ float* jbuf(int b, int comp) const { return scf() + SC::kU + (b * 3 + comp) * NP; }
-  __device__ __forceinline__ float4* at() const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP); }
+  // world axis (a) and torque-like sum (t) of every lane, read back column by column for the kinematic curvature.  One float4
+  // per lane and array, with one float4 of padding after every four lanes: the lanes of a group read four different entries at
+  // a time (one per 4-lane window in block mode), and a stride of 5 float4 puts those on different banks (the interleaved
+  // [lane][a, t] layout of round 1 had every window on the same banks: 23 % of the headline kernel's shared wavefronts)
+  __device__ __forceinline__ float4& at_a(int i) const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP)[i + (i >> 2)]; }
+  __device__ __forceinline__ float4& at_t(int i) const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP)[NP + NP / 4 + i + (i >> 2)]; }
   __device__ __forceinline__ float* lrow() const { return scf() + SC::kU; }
   __device__ __forceinline__ float* hb() const { return scf() + SC::kHb; }
   __device__ __forceinline__ float* lcol() const { return scf() + SC::kLcol; }
@@ -783,16 +788,16 @@ struct Solver {
       {
         const float ar0 = rev ? a[0] : 0.f, ar1 = rev ? a[1] : 0.f, ar2 = rev ? a[2] : 0.f;
         const bool curv_on = rmax < kFarResidual;  // far from the targets the term is large and indefinite
-        at()[2 * l] = make_float4(ar0, ar1, ar2, 0.f);
-        at()[2 * l + 1] = make_float4(t0, t1, t2, 0.f);
+        at_a(l) = make_float4(ar0, ar1, ar2, 0.f);
+        at_t(l) = make_float4(t0, t1, t2, 0.f);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < HN; ++j) {
           if (AR ? (j < 8 ? j < ar_maxw : j - 8 < ar_t) : j < bw) {
             // the joint this register column stands for (arrow mode: clamped; columns a lane does not own add 0 below)
             const int i = AR ? (j < 8 ? (ar_fb + j < NP ? ar_fb + j : NP - 1) : j - 8) : cb + j;
-            const float4 ai = at()[2 * i];
-            const float4 ti_ = at()[2 * i + 1];
+            const float4 ai = at_a(i);
+            const float4 ti_ = at_t(i);
             const bool up = (anc >> i) & 1u;
             const bool dn = (desc >> i) & 1u;
             const float vu = fmaf(ai.x, t0, fmaf(ai.y, t1, ai.z * t2));
@@ -1103,14 +1108,14 @@ struct Solver {
         {
           const bool drop = bad && !accepted && curv_in;
           if (gany<32>(drop, lane)) {
-            const float4 a_self = at()[2 * l];      // (rev ? a : 0), t of this lane, as stored when H was built
-            const float4 t_self = at()[2 * l + 1];
+            const float4 a_self = at_a(l);          // (rev ? a : 0), t of this lane, as stored when H was built
+            const float4 t_self = at_t(l);
 #pragma unroll
             for (int j = 0; j < HN; ++j) {
               if (AR ? (j < 8 ? j < ar_maxw : j - 8 < ar_t) : j < bw) {
                 const int i = AR ? (j < 8 ? (ar_fb + j < NP ? ar_fb + j : NP - 1) : j - 8) : cb + j;
-                const float4 ai = at()[2 * i];
-                const float4 ti_ = at()[2 * i + 1];
+                const float4 ai = at_a(i);
+                const float4 ti_ = at_t(i);
                 const bool up = (anc >> i) & 1u;
                 const bool dn = (desc >> i) & 1u;
                 const float vu = fmaf(ai.x, t_self.x, fmaf(ai.y, t_self.y, ai.z * t_self.z));
