@@ -695,6 +695,45 @@ static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_fra
   return 0;
 }
 
+// Consumer warps per CTA for each solver kind (index = solver_kind()): the register file (64 K x 32 bit per SM, one CTA per
+// SM) gives 128 registers per thread at 15 + 1 warps, 144 at 13 + 1, 168 at 11 + 1.  Measured on B200 (65 536 frames,
+// profiles/r02/warps_sweep.txt): the dense 16-lane solver spills ~50 registers at 128 and runs 19 % faster with 12 warps
+// (LEAP DexPilot 1.72 -> 1.39 ms).  DEXR_FRAMES_WARPS="a,b,c,d" (16 | 14 | 12 per kind) overrides for A/B runs.
+static const int* frames_warps() {
+  static int w[4] = {16, 12, 16, 16};
+  static const bool init = [] {
+    if (const char* e = getenv("DEXR_FRAMES_WARPS")) {
+      int v[4];
+      if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+        for (int i = 0; i < 4; ++i)
+          if (v[i] == 16 || v[i] == 14 || v[i] == 12) w[i] = v[i];
+    }
+    return true;
+  }();
+  (void)init;
+  return w;
+}
+
+template <int G, int BW>
+static int launch_frames_warps(int warps, dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+  if (warps == 12) return launch_frames<G, BW, 11>(r, prm, io, B, stream);
+  if (warps == 14) return launch_frames<G, BW, 13>(r, prm, io, B, stream);
+  return launch_frames<G, BW, 15>(r, prm, io, B, stream);
+}
+
+static int solver_kind(const dexr_table_t& t);
+
+static int launch_frames_kind(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+  const int k = solver_kind(r->host);
+  const int warps = frames_warps()[k];
+  switch (k) {
+    case 0: return launch_frames_warps<16, 4>(warps, r, prm, io, B, stream);   // decoupled 4-joint fingers: block diagonal
+    case 1: return launch_frames_warps<16, 0>(warps, r, prm, io, B, stream);   // dense, 16 lanes
+    case 2: return launch_frames_warps<32, -1>(warps, r, prm, io, B, stream);  // trunk + decoupled fingers: arrow
+    default: return launch_frames_warps<32, 0>(warps, r, prm, io, B, stream);  // dense, 32 lanes
+  }
+}
+
 // Which solver instantiation a table runs on: 0 <16,4> block diagonal, 1 <16,0> dense, 2 <32,-1> arrow, 3 <32,0> dense.
 static int solver_kind(const dexr_table_t& t) {
   if (t.dof <= 16) return t.block_width == 4 ? 0 : 1;
@@ -798,17 +837,7 @@ extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t*
   DEVICE_SCOPE(robot->device);
   dexr_robot* r = const_cast<dexr_robot*>(robot);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  if (t.dof <= 16) {
-    // decoupled 4-joint fingers (Allegro / LEAP vector retargeting): block-diagonal Newton system
-    // (20- and 24-warp variants at 96 / 80 registers were measured slower on B200: 1.86e8 / 1.66e8 against 1.89e8 frames/s)
-    if (t.block_width == 4) return launch_frames<16, 4, 15>(r, params, io, num_frames, stream);
-    return launch_frames<16, 0, 15>(r, params, io, num_frames, stream);
-  }
-  // one frame per warp: 16 warps x 128 registers
-  // trunk + decoupled fingers (Shadow hand, any hand on a free-flying base): arrow factorisation
-  const bool no_arrow = !arrow_enabled();
-  if (t.arrow > 0 && !no_arrow) return launch_frames<32, -1, 15>(r, params, io, num_frames, stream);
-  return launch_frames<32, 0, 15>(r, params, io, num_frames, stream);
+  return launch_frames_kind(r, params, io, num_frames, stream);
 }
 
 template <int G, int BW>

@@ -364,8 +364,10 @@ struct Solver {
   // per lane and array, with one float4 of padding after every four lanes: the lanes of a group read four different entries at
   // a time (one per 4-lane window in block mode), and a stride of 5 float4 puts those on different banks (the interleaved
   // [lane][a, t] layout of round 1 had every window on the same banks: 23 % of the headline kernel's shared wavefronts)
-  __device__ __forceinline__ float4& at_a(int i) const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP)[i + (i >> 2)]; }
-  __device__ __forceinline__ float4& at_t(int i) const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP)[NP + NP / 4 + i + (i >> 2)]; }
+  // (dense and arrow modes read one entry at a time, broadcast to the whole group: plain index there)
+  __device__ __forceinline__ static int at_slot(int i) { return BW > 0 ? i + (i >> 2) : i; }
+  __device__ __forceinline__ float4& at_a(int i) const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP)[at_slot(i)]; }
+  __device__ __forceinline__ float4& at_t(int i) const { return reinterpret_cast<float4*>(scf() + SC::kU + 6 * NP)[NP + NP / 4 + at_slot(i)]; }
   __device__ __forceinline__ float* lrow() const { return scf() + SC::kU; }
   __device__ __forceinline__ float* hb() const { return scf() + SC::kHb; }
   __device__ __forceinline__ float* lcol() const { return scf() + SC::kLcol; }
@@ -373,8 +375,12 @@ struct Solver {
   // q of every joint from the variables: target joints copy, fixed joints constant, mimic affine.
   // (optimizer.py:147-151 + kinematics_adaptor.py:102-105)
   __device__ __forceinline__ float compose_q(float xv) const {
-    const float src = gshfl<G>(xv, msrc >= 0 ? msrc : l);
-    return var >= 0 ? xv : (msrc >= 0 ? fmaf(mmult, src, moff) : qfix);
+    if constexpr (BW != 0) {  // block / arrow tables have neither mimic nor fixed joints (checked on upload): every joint is a
+      return var >= 0 ? xv : 0.f;  // variable, and the mimic / fixed-joint state below is dead (register pressure)
+    } else {
+      const float src = gshfl<G>(xv, msrc >= 0 ? msrc : l);
+      return var >= 0 ? xv : (msrc >= 0 ? fmaf(mmult, src, moff) : qfix);
+    }
   }
 
   // Forward kinematics (robot_wrapper.py:82-83 [pinocchio forwardKinematics]) by pointer jumping.
@@ -585,7 +591,7 @@ struct Solver {
     if (prm.clip_init && var >= 0) xin = fminf(fmaxf(xin, ST().clip_lo[l]), ST().clip_hi[l]);
     x0 = xin;
     x = fminf(fmaxf(xin, lo), hi);
-    const int fixedi = ST().fixed_index[l];
+    const int fixedi = BW != 0 ? -1 : ST().fixed_index[l];
     qfix = (active && fixedi >= 0) ? in.fixed[fixedi] : 0.f;
     bool finite = isfinite(xin) && isfinite(qfix);
     const bool ok_in = prepare_targets(in, active);

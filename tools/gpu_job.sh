@@ -108,3 +108,68 @@ for n in ("default", "prev"):
         print(n, "FAILED", e)
 PY
 fi
+if want ncuab; then
+  for n in default prev; do
+    if [ $n = prev ]; then export DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_prev.so; else unset DEXR_LIBRARY; fi
+    ncu --set full --clock-control none -k regex:dexr_ -s 1 -c 1 -f -o "$out/ab_leapdp_$n" python tools/profile_targets.py leapdp > "$out/ncu_ab_$n.log" 2>&1
+    python tools/ncu_summary.py "$out/ab_leapdp_$n.ncu-rep" "$out/ab_leapdp_$n.md" "$n" > /dev/null 2>&1
+    grep -E "time_duration|inst_executed.sum |issue_active|bank_conflicts|wavefronts_mem_shared" "$out/ab_leapdp_$n.md" | sed "s/^/$n /"
+    sed -n '/warp stall/,/instructions by pipe/p' "$out/ab_leapdp_$n.md" | head -16 | sed "s/^/$n /"
+  done
+  unset DEXR_LIBRARY
+fi
+if want g16d; then
+  for w in 16 12; do
+    DEXR_G16D_WARPS=$w python - <<'PY'
+import os, sys, torch
+sys.path.insert(0, "tools")
+import workloads as W
+dev = torch.device("cuda", 0)
+for key, seed in ((W.LEAP_DEXPILOT_KEY, W.SHADOW_SEED), ("teleop/ability_hand_right", 303), ("teleop/inspire_hand_right", 305)):
+    seq = W.build(key, device=0)
+    kp, x0, f, _ = W.frames(seq, 65536, seed)
+    k, x = torch.from_numpy(kp).to(dev), torch.from_numpy(x0).to(dev)
+    ff = torch.from_numpy(f).to(dev) if f is not None else None
+    out = torch.empty((65536, seq.optimizer.opt_dof), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        seq.optimizer.retarget_batch(keypoints=k, last_qpos=x, fixed_qpos=ff, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        seq.optimizer.retarget_batch(keypoints=k, last_qpos=x, fixed_qpos=ff, out=out)
+    e1.record(); torch.cuda.synchronize()
+    print(f"warps {os.environ['DEXR_G16D_WARPS']}  {key:36s} {e0.elapsed_time(e1) / 10:.4f} ms  {seq.optimizer.engine().launch_info()['block']} threads")
+PY
+  done
+fi
+if want warps; then
+  for cfg in 16,16,16,16 14,14,14,14 12,12,12,12; do
+    DEXR_FRAMES_WARPS=$cfg python - <<'PY'
+import os, sys, torch
+sys.path.insert(0, "tools")
+import workloads as W
+dev = torch.device("cuda", 0)
+cases = [("block16 allegro vector", W.METRIC_KEY, W.METRIC_SEED, {}), ("dense16 leap dexpilot", W.LEAP_DEXPILOT_KEY, W.SHADOW_SEED, {}),
+         ("dense16 ability (mimic)", "teleop/ability_hand_right", 303, {}), ("arrow32 shadow position", W.SHADOW_POS_KEY, W.SHADOW_SEED, dict(narrow_dummy=True)),
+         ("arrow32 shadow vector", "teleop/shadow_hand_right", 301, {}), ("dense32 svh (mimic)", "teleop/schunk_svh_hand_right", 304, {})]
+for name, key, seed, kw in cases:
+    seq = W.build(key, device=0)
+    sets = []
+    for s in range(4):
+        kp, x0, f, _ = W.frames(seq, 65536, seed + 1000 * s, **kw)
+        sets.append((torch.from_numpy(kp).to(dev), torch.from_numpy(x0).to(dev), torch.from_numpy(f).to(dev) if f is not None else None))
+    out = torch.empty((65536, seq.optimizer.opt_dof), dtype=torch.float32, device=dev)
+    for i in range(4):
+        seq.optimizer.retarget_batch(keypoints=sets[i][0], last_qpos=sets[i][1], fixed_qpos=sets[i][2], out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(12):
+        k, x, f = sets[i % 4]
+        seq.optimizer.retarget_batch(keypoints=k, last_qpos=x, fixed_qpos=f, out=out)
+    e1.record(); torch.cuda.synchronize()
+    print(f"warps {os.environ['DEXR_FRAMES_WARPS']:12s} {name:28s} {e0.elapsed_time(e1) / 12:.4f} ms  ({seq.optimizer.engine().launch_info()['block']} threads)")
+PY
+  done 2>&1 | tee "$out/warps_sweep.txt"
+fi
