@@ -22,12 +22,12 @@ pytestmark = pytest.mark.gpu
 
 # tag, config key, batch the workload is generated at, seed, generator options, same-basin floor (measured on B200, see module doc)
 FRAME_CASES = [
-    ("metric", W.METRIC_KEY, 65536, W.METRIC_SEED, {}, 0.995),
-    ("metric_cold", W.METRIC_KEY, 65536, W.METRIC_SEED, dict(sigma=0.5), 0.80),
-    ("shadow_narrow", W.SHADOW_POS_KEY, 65536, W.SHADOW_SEED, dict(narrow_dummy=True), 0.99),
-    ("shadow_ship", W.SHADOW_POS_KEY, 65536, W.SHADOW_SEED, dict(narrow_dummy=False), 0.99),
-    ("leap_frames", W.LEAP_DEXPILOT_KEY, 65536, W.SHADOW_SEED, {}, 0.99),
-] + [(f"mixed/{k.split('/')[1]}", k, 16384, W.MIXED_SEED + i, {}, 0.99) for i, k in enumerate(W.MIXED_KEYS)]
+    ("metric", W.METRIC_KEY, 65536, W.METRIC_SEED, {}, 0.999),                            # measured on B200: 1.0000 (4096 frames)
+    ("metric_cold", W.METRIC_KEY, 65536, W.METRIC_SEED, dict(sigma=0.5), 0.995),          # 1.0000 (1024)
+    ("shadow_narrow", W.SHADOW_POS_KEY, 65536, W.SHADOW_SEED, dict(narrow_dummy=True), 0.999),   # 1.0000 (4096)
+    ("shadow_ship", W.SHADOW_POS_KEY, 65536, W.SHADOW_SEED, dict(narrow_dummy=False), 0.995),    # 1.0000 (1024)
+    ("leap_frames", W.LEAP_DEXPILOT_KEY, 65536, W.SHADOW_SEED, {}, 0.993),                # 0.9971 (2048): 6 frames in other minima
+] + [(f"mixed/{k.split('/')[1]}", k, 16384, W.MIXED_SEED + i, {}, 0.995) for i, k in enumerate(W.MIXED_KEYS)]  # 1.0000 (256 each)
 
 
 def _solve(seq, kp, x0, fixed):
@@ -87,7 +87,7 @@ def test_metric_real_trajectory_matches_oracle():
     q, st = _solve(seq, kp[:n], x0[:n], None)
     rec = P.compare("metric_real", q, W.digest(kp[:n], x0[:n], None), st)
     print(rec)
-    assert "error" not in rec and rec["max_within_basin"] < P.TOL and rec["same_basin"] >= 0.90, rec
+    assert "error" not in rec and rec["max_within_basin"] < P.TOL and rec["same_basin"] >= 0.995, rec  # measured 1.0000 (1242)
 
 
 def _run_streams(S):

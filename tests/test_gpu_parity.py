@@ -77,6 +77,7 @@ def check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin):
         obj = o.make_objective(refs[i], fixed[i], x0[i], update_state=False)
         xp, kkt = polish(obj, q[i], o.lower, o.upper)
         assert kkt < 1e-6 and np.abs(xp - q[i]).max() < TOL, f"frame {i}: GPU answer is not a minimiser (moved {np.abs(xp - q[i]).max():.2e})"
+    print(f"same basin {same.mean():.4f} of {len(same)} (floor {min_same_basin}), |dq| median {np.median(dq):.1e} max inside {dq[same].max() if same.any() else float('nan'):.1e}")
     assert same.mean() >= min_same_basin, f"only {same.mean():.3f} of frames in the oracle's basin"
     # reported cost is the consistent objective at the returned point
     for i in range(0, len(q), max(1, len(q) // 8)):
@@ -112,7 +113,9 @@ def test_synthetic_warm_start_parity(key, ov):
     refs, fixed, x0, _ = synth_problems(o, 24, rng, init_noise=0.05, target_noise=0.01)
     XB, FB = oracle_b(o, refs, fixed, x0)
     res = gpu_solve(seq.optimizer, refs, fixed, x0)
-    dq = check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.9)
+    # measured (printed by check_against_oracle): 24 of 24 frames in the oracle's basin for every family except
+    # offline/shadow_hand_right (23 of 24; the 24th is verified above to be another minimiser)
+    dq = check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.95)
     assert np.median(dq) < 1e-5
 
 
@@ -294,7 +297,7 @@ def test_bounds_are_respected_and_active():
     refs = (refs * 1.25).astype(np.float32)  # x 1.6 config scaling = 2x the robot's reach
     XB, FB = oracle_b(o, refs, fixed, x0)
     res = gpu_solve(seq.optimizer, refs, fixed, x0)
-    check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.8)
+    check_against_oracle(o, res, refs, fixed, x0, XB, FB, min_same_basin=0.93)  # measured: 16 of 16
     on_bound = (np.abs(res["q"] - o.lower) < 1e-6) | (np.abs(res["q"] - o.upper) < 1e-6)
     assert on_bound.any()
 
