@@ -334,7 +334,8 @@ struct Solver {
 
   // ---- per-frame state ----
   float x, x0, q, qfix;       // variable value, anchor, full joint value, fixed value
-  float R[9], p[3], a[3];     // world placement of this joint frame, world axis (at accepted x)
+  float p[3], a[3];           // world origin of this joint frame and world axis at the accepted x (the 3x3 world rotation is
+                              // transient: it only serves to place the links and to rotate the axis, right after an FK)
   float F;                    // objective at x
   float Fl;                   // this lane's term of F at x (residual l and / or the regulariser of variable l): trial points
                               // are compared term by term, sum_l (v_new - v_old), which resolves differences far below ulp(F)
@@ -428,6 +429,14 @@ struct Solver {
         for (int i = 0; i < 3; ++i) po[i] = pn[i];
       }
     }
+  }
+
+  // World axis of this lane's joint from its world rotation (the Jacobian column direction, robot_wrapper.py:93-95).
+  __device__ __forceinline__ void set_world_axis(const float* Rw) {
+    const float ax0 = ST().lane_c[6][l].w, ax1 = ST().lane_c[7][l].w, ax2 = ST().lane_c[8][l].w;
+    a[0] = fmaf(Rw[0], ax0, fmaf(Rw[1], ax1, Rw[2] * ax2));
+    a[1] = fmaf(Rw[3], ax0, fmaf(Rw[4], ax1, Rw[5] * ax2));
+    a[2] = fmaf(Rw[6], ax0, fmaf(Rw[7], ax1, Rw[8] * ax2));
   }
 
   // Link origins (robot_wrapper.py:85-87 [updateFramePlacement]) -> shared buffer b.  Each lane places the links
@@ -605,10 +614,14 @@ struct Solver {
       active = false;
     }
     q = compose_q(x);
-    fk(q, R, p);
-    cur = 0;
-    write_world_links();
-    write_links(R, p, cur);
+    {
+      float R[9];
+      fk(q, R, p);
+      cur = 0;
+      write_world_links();
+      write_links(R, p, cur);
+      set_world_axis(R);
+    }
     __syncwarp();
     cost(cur, x);
     Fnz = cost_nz;
@@ -661,12 +674,6 @@ struct Solver {
 #pragma unroll
       for (int i = 0; i < HN; ++i) H[i] = 0.f;
       float g = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
-      {
-        const float ax0 = ST().lane_c[6][l].w, ax1 = ST().lane_c[7][l].w, ax2 = ST().lane_c[8][l].w;
-        a[0] = fmaf(R[0], ax0, fmaf(R[1], ax1, R[2] * ax2));
-        a[1] = fmaf(R[3], ax0, fmaf(R[4], ax1, R[5] * ax2));
-        a[2] = fmaf(R[6], ax0, fmaf(R[7], ax1, R[8] * ax2));
-      }
       const bool rev = jtype == 0;
       const int m = dm.n_res;
       const int loss = dm.loss;
@@ -1176,8 +1183,7 @@ struct Solver {
             x = xn; q = qn; F = Fn;
             Fnz = cost_nz;
             Fl = cost_lane;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+            set_world_axis(Rn);
 #pragma unroll
             for (int i = 0; i < 3; ++i) p[i] = pn[i];
             cur ^= 1;
