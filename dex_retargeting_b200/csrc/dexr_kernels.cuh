@@ -134,6 +134,18 @@ __device__ __forceinline__ float fast_rsqrt(float x) {
 #endif
 }
 
+// 1 / x for normal positive x: the bare MUFU.RCP (rcp.approx.ftz, 1 ulp) instead of the 8-9 instruction sequences behind
+// __fdividef / __frcp_rn; the callers exclude zero and denormal arguments
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifndef DEXR_HOST_EMULATION
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
 __device__ __forceinline__ float huber_val(float d, float beta, float inv_beta) {
   return d < beta ? 0.5f * d * d * inv_beta : d - 0.5f * beta;
 }
@@ -730,16 +742,16 @@ struct Solver {
           rmax = on ? fmaxf(rmax, fmaxf(ax_, fmaxf(ay_, az_))) : rmax;
           // 1/beta exactly inside the quadratic zone; beyond it the fast reciprocal (<= 2 ulp) is plenty: it only
           // scales a unit-magnitude gradient component and the majoriser curvature
-          const float wx = ax_ < beta ? inv_beta : __fdividef(1.0f, ax_);
-          const float wy = ay_ < beta ? inv_beta : __fdividef(1.0f, ay_);
-          const float wz = az_ < beta ? inv_beta : __fdividef(1.0f, az_);
+          const float wx = ax_ < beta ? inv_beta : fast_rcp(ax_);
+          const float wy = ay_ < beta ? inv_beta : fast_rcp(ay_);
+          const float wz = az_ < beta ? inv_beta : fast_rcp(az_);
           gx = T.w * rx * wx; gy = T.w * ry * wy; gz = T.w * rz * wz;
           y0 = T.w * wx * j0; y1 = T.w * wy * j1; y2 = T.w * wz * j2;
         } else {
           const float d = sqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
           rmax = on ? fmaxf(rmax, d) : rmax;
           const bool quad = d < beta;
-          const float invd = d > 0.f ? __frcp_rn(d) : 0.f;
+          const float invd = d > 1e-30f ? fast_rcp(d) : 0.f;
           const float ux = rx * invd, uy = ry * invd, uz = rz * invd;
           const float hp = quad ? d * inv_beta : 1.0f;
           gx = T.w * hp * ux; gy = T.w * hp * uy; gz = T.w * hp * uz;
@@ -772,6 +784,8 @@ struct Solver {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j < ar_maxw) {
+              // (the clamp costs two instructions per column; without it ptxas keeps more addresses live and spills 24 bytes
+              // more in the 128-register arrow kernel: Shadow position 3.43 -> 3.75 ms on B200)
               const int cj = ar_fb + j < NP ? ar_fb + j : NP - 1;
               const float v = fmaf(jbuf(b, 0)[cj], y0, fmaf(jbuf(b, 1)[cj], y1, jbuf(b, 2)[cj] * y2));
               H[j] += j < ar_fw ? v : 0.f;
@@ -959,7 +973,7 @@ struct Solver {
               if (act && pk == l) hk += fmaf(lam, D, reg2);
               const float dkk = gshfl<G>(hk, act ? pk : l);
               bad = bad || (act && !(dkk > 1e-20f));
-              const float inv = act ? rsqrtf(fmaxf(dkk, 1e-20f)) : 1.0f;
+              const float inv = act ? fast_rsqrt(fmaxf(dkk, 1e-20f)) : 1.0f;
               const float lik = hk * inv;                            // L[l][pk] for l >= pk
               const float yk = gshfl<G>(y, act ? pk : l) * inv;      // forward substitution fused
               const bool piv = act && l == pk, below = act && l > pk;
