@@ -43,6 +43,7 @@ struct SeqArgs {
   int scratch_off;
   int spw;  // streams per warp: 32 / G when streams are plentiful; 1 when they are scarce (a stream is latency bound, and two
             // streams sharing a warp both pay the larger of their two iteration counts on every frame)
+  int duo;  // spw == 1 with a 16-lane solver: the second half-warp works on the SAME stream (Solver::duo) instead of idling
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -228,12 +229,15 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   const int lane = threadIdx.x & 31;
   const int gid = warp * GPW + (lane / G);               // scratch slot of this group of lanes
   const int slot = a.spw == GPW ? gid : warp;            // which of the CTA's stream slots this group serves
-  const bool owner = a.spw == GPW || (lane / G) == 0;    // (scarce streams: only the first group of a warp carries one)
+  const bool first = (lane / G) == 0;
+  const bool owner = a.spw == GPW || first;              // the group that reads and writes the stream's state
+  const bool works = owner || a.duo;                     // (scarce streams, 16 lanes: the second half-warp helps the first)
   const int slots_per_cta = NW * a.spw;
   const uint32_t scratch_off = (uint32_t)(a.scratch_off + gid * (Scratch<G>::kFloats + 64) * 4);
   float* kpbuf = reinterpret_cast<float*>(smem + scratch_off) + Scratch<G>::kFloats;  // 63 floats: current keypoints
   Solver<G, BW> sv;
   sv.init(a.table, a.dm, scratch_off, a.prm, lane);
+  if (G == 16 && a.duo) sv.duo = lane / G;
   const int l = sv.l;
   const bool use_filter = a.prm.lp_alpha >= 0.f && a.prm.lp_alpha <= 1.f;
 
@@ -242,8 +246,9 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
   for (long long base = 0; base < a.S; base += (long long)gridDim.x * slots_per_cta) {
     // all groups of a warp must walk the time loop together (warp-wide shuffles inside solve)
     const long long s = base + (long long)slot * gridDim.x + blockIdx.x;
-    const bool active = owner && s < a.S;
-    const long long sc = (owner && s < a.S) ? s : a.S - 1;
+    const bool active = works && s < a.S;   // solves (and, in duo mode, reads the same state as the owner half)
+    const bool writes = owner && s < a.S;   // stores results and state
+    const long long sc = active ? s : a.S - 1;
     float last = 0.f, fy = 0.f;
     int finit = 0;
     if (active && sv.var >= 0) last = a.io.last_qpos[sc * a.dm.n_var + sv.var];
@@ -287,13 +292,13 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
         finit = 1;
         out = fy;
       }
-      if (active) {
+      if (writes) {
         if (l < a.dm.dof) a.io.robot_qpos_out[(sc * a.steps + t) * a.dm.dof + l] = out;
         if (l == 0 && a.io.status_out) a.io.status_out[sc * a.steps + t] = status;
       }
       __syncwarp();
     }
-    if (active) {
+    if (writes) {
       if (sv.var >= 0) a.io.last_qpos[sc * a.dm.n_var + sv.var] = last;
       if (use_filter && l < a.dm.dof) a.io.filter_state[sc * a.dm.dof + l] = fy;
       if (use_filter && l == 0) a.io.filter_init[sc] = (uint8_t)finit;
@@ -865,6 +870,8 @@ static int launch_sequences(dexr_robot* r, const dexr_params_t* prm, const dexr_
   a.spw = (GPW > 1 && S > warps_one_wave) ? GPW : 1;
   static const int spw_env = [] { const char* e = getenv("DEXR_SEQ_PAIR"); return e ? atoi(e) : -1; }();  // A/B: 1 = always pair
   if (spw_env == 1) a.spw = GPW;
+  const char* duo_env = getenv("DEXR_SEQ_DUO");  // 0 = off (read per call: tests compare the two modes in one process)
+  a.duo = (G == 16 && a.spw == 1 && !(duo_env && atoi(duo_env) == 0)) ? 1 : 0;
   const long long per_cta = (long long)kSeqNW * a.spw;
   const long long ctas = std::max<long long>(1, (S + a.spw - 1) / a.spw);  // at least one warp's worth of streams per CTA
   int grid = (int)std::min<long long>(ctas, (long long)r->num_sms * (S >= (long long)r->num_sms * per_cta * 2 ? 2 : 1));

@@ -355,6 +355,11 @@ struct Solver {
   mutable float cost_nz;      // the same for the last cost() call
   mutable float cost_lane;    // this lane's term for the last cost() call
   int cur;                    // which link-position buffer holds the accepted positions
+  int duo = -1;               // 16-lane solver only: -1 = this group owns its frame; 0 / 1 = BOTH groups of the warp work on the same
+                              // frame (scarce streams: a stream is latency bound, the second half-warp would idle) and this is
+                              // half `duo`: the merged residual passes are dealt alternately to the two halves -- same
+                              // instructions, other residuals -- and their partial gradient / Hessian sums are added across the
+                              // halves with full-width shuffles.  Everything else runs redundantly in both halves.
 
   __device__ __forceinline__ static const SharedTable& ST() { return *reinterpret_cast<const SharedTable*>(dsmem); }
 
@@ -701,12 +706,16 @@ struct Solver {
       constexpr bool merged = !AR;  // merged residual passes (arrow mode keeps one residual per pass)
       int trips = m;
       if constexpr (merged) trips = ST().n_pass;
+      const bool two_halves = merged && G == 16 && duo >= 0;
+      const int n_pass = trips;
+      if (two_halves) trips = (trips + 1) >> 1;
       for (int kk = 0; kk < trips; ++kk) {
         int k = kk;
         bool on = true;  // merged mode: false on the lanes of a slot that has no residual in this pass
         if constexpr (merged) {
-          const int kw = ST().pass_res[kk][l / (BW > 0 ? BW : 4)];
-          on = kw >= 0;
+          const int kq = two_halves ? 2 * kk + duo : kk;       // this half's pass
+          const int kw = ST().pass_res[kq < n_pass ? kq : 0][l / (BW > 0 ? BW : 4)];
+          on = kq < n_pass && kw >= 0;
           k = on ? kw : 0;
         }
         const int ti = ST().res_task[k], oi = ST().res_origin[k];
@@ -807,6 +816,17 @@ struct Solver {
         }
       }
       if constexpr (merged) rmax = gmax<G>(rmax);  // every window saw only its own residuals
+      if constexpr (merged && G == 16) {
+        if (two_halves) {  // add the other half's passes (warp-uniform branch: both halves of a warp are in this mode or neither)
+          rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 16));
+          g += __shfl_xor_sync(0xffffffffu, g, 16);
+          t0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+          t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+          t2 += __shfl_xor_sync(0xffffffffu, t2, 16);
+#pragma unroll
+          for (int i = 0; i < HN; ++i) H[i] += __shfl_xor_sync(0xffffffffu, H[i], 16);
+        }
+      }
       if constexpr (AR) {  // the aligned trunk chunks also swept columns ar_t..7 (finger lanes): not trunk couplings
 #pragma unroll
         for (int c = 0; c < 8; ++c) H[8 + c] = c < ar_t ? H[8 + c] : 0.f;

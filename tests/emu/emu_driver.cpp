@@ -175,6 +175,7 @@ struct SeqJob {
   dexr_sequences_t io;
   long long S, base;
   int T;
+  int duo;  // 16-lane solver: both groups of the warp work on stream `base` (dexr_sequences_kernel with spw == 1)
 } sjob;
 
 template <int G, int BW>
@@ -184,10 +185,13 @@ void seq_lane_body(int lane) {
   const int gid = lane / G;
   Solver<G, BW> sv;
   sv.init(j.tb, j.dm, (uint32_t)(j.scratch_off + gid * Scratch<G>::kFloats * 4), j.prm, lane);
+  const bool duo = G == 16 && q.duo;
+  if (duo) sv.duo = gid;
   const int l = sv.l;
   const bool use_filter = j.prm.lp_alpha >= 0.f && j.prm.lp_alpha <= 1.f;
-  const long long s = q.base + gid;
+  const long long s = duo ? q.base : q.base + gid;
   const bool active = s < q.S;
+  const bool writes = active && (!duo || gid == 0);
   const long long sc = active ? s : q.S - 1;
   float last = 0.f, fy = 0.f;
   int finit = 0;
@@ -210,13 +214,13 @@ void seq_lane_body(int lane) {
       finit = 1;
       out = fy;
     }
-    if (active) {
+    if (writes) {
       if (l < j.dm.dof) q.io.robot_qpos_out[(sc * q.T + t) * j.dm.dof + l] = out;
       if (l == 0 && q.io.status_out) q.io.status_out[sc * q.T + t] = status;
     }
     __syncwarp();
   }
-  if (active) {
+  if (writes) {
     if (sv.var >= 0) q.io.last_qpos[sc * j.dm.n_var + sv.var] = last;
     if (use_filter && l < j.dm.dof) q.io.filter_state[sc * j.dm.dof + l] = fy;
     if (use_filter && l == 0) q.io.filter_init[sc] = (uint8_t)finit;
@@ -230,7 +234,7 @@ int run_streams(char* err, int errlen) {
   const int scratch_bytes = GPW * Scratch<G>::kFloats * 4;
   threadIdx.x = 0; blockDim.x = 1;
   load_shared_table(*reinterpret_cast<SharedTable*>(dsmem), job.tb);
-  for (sjob.base = 0; sjob.base < sjob.S; sjob.base += GPW) {
+  for (sjob.base = 0; sjob.base < sjob.S; sjob.base += (G == 16 && sjob.duo) ? 1 : GPW) {
     uint32_t* sc = reinterpret_cast<uint32_t*>(dsmem + job.scratch_off);
     for (int i = 0; i < scratch_bytes / 4; ++i) sc[i] = 0x7fc00000u;
     if (emu::run_warp(&seq_lane_body<G, BW>) != 0) {
@@ -243,7 +247,7 @@ int run_streams(char* err, int errlen) {
 }  // namespace
 
 extern "C" int emu_solve_sequences(const dexr_table_t* tb, const dexr_params_t* prm, int use_arrow, const dexr_sequences_t* io,
-                                   long long S, long long T, char* err, int errlen) {
+                                   long long S, long long T, int duo, char* err, int errlen) {
   job = Job{};
   job.tb = tb; job.prm = *prm;
   job.prm.clip_init = 1;  // launch_sequences: SeqRetargeting.retarget always clips the warm start
@@ -251,7 +255,7 @@ extern "C" int emu_solve_sequences(const dexr_table_t* tb, const dexr_params_t* 
   d.dof = tb->dof; d.n_var = tb->n_var; d.n_fixed = tb->n_fixed; d.n_links = tb->n_links; d.n_res = tb->n_res; d.loss = tb->loss;
   d.n_rounds = tb->n_rounds; d.has_mimic = tb->has_mimic; d.num_fingers = tb->num_fingers; d.len_proj = tb->len_proj;
   d.len_s1 = tb->len_s1; d.block_width = tb->block_width; d.trunk = tb->arrow > 0 ? tb->arrow - 1 : 0;
-  sjob.io = *io; sjob.S = S; sjob.T = (int)T;
+  sjob.io = *io; sjob.S = S; sjob.T = (int)T; sjob.duo = duo;
   if (S <= 0 || T <= 0) return 0;
   if (tb->dof <= 16) return tb->block_width == 4 ? run_streams<16, 4>(err, errlen) : run_streams<16, 0>(err, errlen);
   if (tb->arrow > 0 && use_arrow) return run_streams<32, -1>(err, errlen);

@@ -66,9 +66,10 @@ def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None
     return (out, status, cost, full) if want_robot_qpos else (out, status, cost)
 
 
-def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_hand=None):
+def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_hand=None, duo=False):
     """Emulated dexr_solve_sequences for a SeqRetargeting of the host mirror: keypoints [S,T,21,3] -> filtered robot qpos
-    [S,T,dof]; `state` = dict(last_qpos, filter_state, filter_init, projected) carried between calls (created if None)."""
+    [S,T,dof]; `state` = dict(last_qpos, filter_state, filter_init, projected) carried between calls (created if None).
+    `duo`: the scarce-streams mode of the 16-lane solver (both half-warps on one stream, residual passes split)."""
     from dex_retargeting_b200 import _native as N
 
     lib = load(tuple(defines))
@@ -91,7 +92,7 @@ def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_
     err = C.create_string_buffer(600)
     lib.emu_solve_sequences.restype = C.c_int
     rc = lib.emu_solve_sequences(C.byref(table), C.byref(prm), C.c_int(int(use_arrow)), C.byref(io), C.c_longlong(S),
-                                 C.c_longlong(T), err, C.c_int(600))
+                                 C.c_longlong(T), C.c_int(int(duo)), err, C.c_int(600))
     if rc != 0:
         raise RuntimeError(f"host emulation failed ({rc}): {err.value.decode()}")
     return out, status, state

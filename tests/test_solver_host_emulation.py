@@ -260,3 +260,20 @@ def test_fused_keypoint_preprocessing_matches_detector_oracle(key, hand):
         xb = solve_converged(o, o.ref_from_keypoints(kp.astype(np.float32)), np.zeros(nf), x0[b], update_state=False)[0]
         inside += np.abs(q[b] - xb).max() < TOL
     assert inside >= B - 2, inside  # mid-range cold start on recorded frames: an occasional other basin
+
+
+@pytest.mark.parametrize("key", ["teleop/leap_hand_right_dexpilot", "teleop/ability_hand_right", "teleop/allegro_hand_right"])
+def test_two_half_warps_on_one_stream_match_the_single_group(key):
+    """Scarce streams (dexr_sequences_kernel with one stream per warp): the second 16-lane group of the warp works on the SAME
+    stream and takes every other merged residual pass; the partial gradient / Hessian sums are added across the halves.  Same
+    mathematics, another summation order: the trajectories agree to rounding and the DexPilot flags exactly."""
+    seq = build_product(key)
+    kp = keypoint_trajectory()[None, 100:140].astype(np.float32)
+    kp = np.concatenate([kp, kp[:, ::-1]], 0)  # two streams
+    a, sa, st_a = emu_host.solve_sequences(seq, kp)
+    b, sb, st_b = emu_host.solve_sequences(seq, kp, duo=True)
+    assert np.all((sb >> 24) == 0)
+    d = np.abs(a - b).max(2)
+    assert np.median(d) < 1e-6 and (d < 1e-4).mean() > 0.97, (np.median(d), d.max())
+    if st_a["projected"] is not None:
+        np.testing.assert_array_equal(st_a["projected"], st_b["projected"])
