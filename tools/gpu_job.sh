@@ -173,3 +173,31 @@ for name, key, seed, kw in cases:
 PY
   done 2>&1 | tee "$out/warps_sweep.txt"
 fi
+if want tiles; then
+  for n in default prev; do
+    if [ $n = prev ]; then export DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_prev.so; else unset DEXR_LIBRARY; fi
+    python - <<'PY'
+import os, sys, torch
+sys.path.insert(0, "tools")
+import workloads as W
+dev = torch.device("cuda", 0)
+tag = "prev" if os.environ.get("DEXR_LIBRARY") else "new "
+for key, seed, kw in ((W.SHADOW_POS_KEY, W.SHADOW_SEED, dict(narrow_dummy=True)), (W.METRIC_KEY, W.METRIC_SEED, {}), (W.LEAP_DEXPILOT_KEY, W.SHADOW_SEED, {})):
+    seq = W.build(key, device=0)
+    for B in (2048, 8192, 16384, 32768):
+        kp, x0, f, _ = W.frames(seq, B, seed, **kw)
+        k, x = torch.from_numpy(kp).to(dev), torch.from_numpy(x0).to(dev)
+        out = torch.empty((B, seq.optimizer.opt_dof), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            seq.optimizer.retarget_batch(keypoints=k, last_qpos=x, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            seq.optimizer.retarget_batch(keypoints=k, last_qpos=x, out=out)
+        e1.record(); torch.cuda.synchronize()
+        print(f"{tag} {key:34s} B {B:6d}: {e0.elapsed_time(e1) / 20:.4f} ms  tile {seq.optimizer.engine().launch_info()['frames_per_tile']}")
+PY
+  done
+  unset DEXR_LIBRARY
+fi
