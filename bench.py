@@ -367,8 +367,23 @@ def main():
     for s in range(3):
         opt.retarget_batch_host(keypoints=sets[s % 2][0], last_qpos=sets[s % 2][1], out=out_page)
     staged_ms = (time.perf_counter() - t0) * 1e3 / 3
+    # the same frames in the form Optimizer.retarget() itself receives (optimizer.py:47): ref_value [B,m,3] = the caller-side
+    # gather keypoints[task] - keypoints[origin] (example/vector_retargeting/single_hand_detector usage), 48 B instead of 252 B
+    hi = np.asarray(opt.target_link_human_indices)
+    rv_pin = [torch.from_numpy(np.ascontiguousarray(sets[i][0][:, hi[1]] - sets[i][0][:, hi[0]])).pin_memory() for i in range(2)]
+    out_rv = torch.empty((B, opt.opt_dof), dtype=torch.float32).pin_memory()
+    for s in range(2):
+        opt.retarget_batch_host(ref_value=rv_pin[s % 2], last_qpos=x0_pin[s % 2], out=out_rv)
+    rv_same = float((out_rv - out_pin).abs().max()) if e2e_steps % 2 == 0 else float("nan")
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        opt.retarget_batch_host(ref_value=rv_pin[s % 2], last_qpos=x0_pin[s % 2], out=out_rv)
+    torch.cuda.synchronize(dev)
+    rv_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    rv_bytes = int(rv_pin[0][0].numel()) * 4
 
-    times = {"total_ms": total_ms, "e2e_ms": e2e_ms, "sus_ms": sus_ms, "staged_ms": staged_ms}
+    times = {"total_ms": total_ms, "e2e_ms": e2e_ms, "sus_ms": sus_ms, "staged_ms": staged_ms, "rv_ms": rv_ms}
 
     # ---- per-configuration records ---------------------------------------------------------------
     records = []  # (record dict, time key)
@@ -503,7 +518,10 @@ def main():
         torch.cuda.synchronize(dev)
         rec = {"name": "mixed_robots", "baseline_config": 5, "scaling": "strong", "global_frames": per * len(jobs), "frames_per_gpu": (e - b) * len(jobs),
                "robots": [j[6] for j in jobs], "bytes_per_frame": sum(bytes_per_frame(j[0]) for j in jobs) / len(jobs), "reps": 5,
-               "launches_per_step": 1, "note": "one persistent launch over the six robot groups (dexr_solve_frames_multi)",
+               "launches_per_step": 1 if os.environ.get("DEXR_MULTI_MODE") == "persistent" else len(jobs),
+               "note": "ONE call, dexr_solve_frames_multi: the six robot groups run as concurrent standalone kernels forked onto library side "
+                       "streams and joined by events (default), or as one persistent kernel with DEXR_MULTI_MODE=persistent (measured slower, "
+                       "profiles/r02/mixed_launch_sweep.txt)",
                "six_launches_ms_this_rank": ms_six}
         if rank == 0:
             pr = []
@@ -523,6 +541,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times = {k: float(v) for k, v in zip(keys, t.tolist())}
     total_ms, e2e_ms, sus_ms, staged_ms = times["total_ms"], times["e2e_ms"], times["sus_ms"], times["staged_ms"]
+    rv_ms = times["rv_ms"]
 
     if rank == 0:
         peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -595,7 +614,12 @@ def main():
                            "kernel's TMA producer pulls the input tiles from host memory over PCIe and the results are "
                            "stored straight to host memory, all inside the timed region",
                     "staged_pageable": {"value": B * world / (staged_ms * 1e-3), "unit": "frames/s", "ms_per_step": staged_ms, "steps": 3,
-                                        "api": "same call, pageable numpy buffers: 4-chunk H2D -> solve -> D2H pipeline on two internal streams"}},
+                                        "api": "same call, pageable numpy buffers: 4-chunk H2D -> solve -> D2H pipeline on two internal streams"},
+                    "ref_value_form": {"value": B * world / (rv_ms * 1e-3), "unit": "frames/s", "ms_per_step": rv_ms, "steps": e2e_steps,
+                                       "h2d_bytes_per_step": B * (rv_bytes + 64), "d2h_bytes_per_step": B * 64,
+                                       "max_abs_diff_vs_keypoint_form_rad": rv_same,
+                                       "api": "same call with ref_value [B,m,3] (what Optimizer.retarget receives, the gather done by "
+                                              "the caller outside the timed region) instead of the 21 keypoints; NOT the headline form"}},
             "gpu_launches": args.steps, "clocks": clk.summary(),
             "solver": {"mean_iterations": iters_mean, "frames_flagged": flagged, "launch": opt.engine().launch_info(), "build_id": build_id},
             "parity": parity, "configs": records,

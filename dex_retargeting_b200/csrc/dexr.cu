@@ -655,7 +655,7 @@ static bool arrow_enabled() {
 // Fill the kernel arguments of one robot group: tile size, ring layout, dynamic shared memory.  `slots` = CTAs the tiles are
 // spread over.  Returns the dynamic shared memory the group needs.
 template <int G, int NCW>
-static int fill_frame_args(const dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, int slots, FrameArgs& a) {
+static int fill_frame_args(const dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, int slots, FrameArgs& a, int tile = 0) {
   const dexr_table_t& t = r->host;
   a = FrameArgs{};
   a.table = r->table_dev;
@@ -671,6 +671,12 @@ static int fill_frame_args(const dexr_robot* r, const dexr_params_t* prm, const 
   const long long rounds = std::max<long long>(1, (per + FramesCfg<G>::kMaxTile - 1) / FramesCfg<G>::kMaxTile);
   int T = (int)std::min<long long>(FramesCfg<G>::kMaxTile, std::max<long long>(4, (per + rounds - 1) / rounds));
   T = round_up(T, 4);
+  // A CTA solves NCW x (32 / G) frames at a time.  When its whole share fits one such round, rounding the tile up to the
+  // bulk-copy granularity must not push it into a second, nearly empty round (Shadow, 2048 frames: 14 per CTA -> 16 on 15
+  // warps): keep the exact count, the producer then stages the tile with plain loads.
+  constexpr int kRound = NCW * (32 / G);
+  if (per <= kRound && T > kRound) T = (int)per;
+  if (tile > 0) T = std::min(tile, FramesCfg<G>::kMaxTile);  // mixed launches size the tiles of all groups together
   a.T = T;
   a.ntiles = (int)((B + T - 1) / T);
   auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
@@ -688,10 +694,10 @@ static int fill_frame_args(const dexr_robot* r, const dexr_params_t* prm, const 
 }
 
 template <int G, int BW, int NCW>
-static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+static int launch_frames(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream, int slots, int tile) {
   FrameArgs a;
-  const int slots = r->num_sms;  // one CTA per SM
-  const int smem = fill_frame_args<G, NCW>(r, prm, io, B, slots, a);
+  if (slots <= 0) slots = r->num_sms;  // one persistent CTA per SM; a mixed launch passes its own CTA count and tile size
+  const int smem = fill_frame_args<G, NCW>(r, prm, io, B, slots, a, tile);
   auto kern = dexr_frames_kernel<G, BW, NCW>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(a.ntiles, slots);
@@ -724,22 +730,23 @@ static const int* frames_warps() {
 }
 
 template <int G, int BW>
-static int launch_frames_warps(int warps, dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
-  if (warps == 12) return launch_frames<G, BW, 11>(r, prm, io, B, stream);
-  if (warps == 14) return launch_frames<G, BW, 13>(r, prm, io, B, stream);
-  return launch_frames<G, BW, 15>(r, prm, io, B, stream);
+static int launch_frames_warps(int warps, dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream, int slots, int tile) {
+  if (warps == 12) return launch_frames<G, BW, 11>(r, prm, io, B, stream, slots, tile);
+  if (warps == 14) return launch_frames<G, BW, 13>(r, prm, io, B, stream, slots, tile);
+  return launch_frames<G, BW, 15>(r, prm, io, B, stream, slots, tile);
 }
 
 static int solver_kind(const dexr_table_t& t);
 
-static int launch_frames_kind(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream) {
+static int launch_frames_kind(dexr_robot* r, const dexr_params_t* prm, const dexr_frames_t* io, long long B, cudaStream_t stream,
+                              int slots = 0, int tile = 0) {
   const int k = solver_kind(r->host);
   const int warps = frames_warps()[k];
   switch (k) {
-    case 0: return launch_frames_warps<16, 4>(warps, r, prm, io, B, stream);   // decoupled 4-joint fingers: block diagonal
-    case 1: return launch_frames_warps<16, 0>(warps, r, prm, io, B, stream);   // dense, 16 lanes
-    case 2: return launch_frames_warps<32, -1>(warps, r, prm, io, B, stream);  // trunk + decoupled fingers: arrow
-    default: return launch_frames_warps<32, 0>(warps, r, prm, io, B, stream);  // dense, 32 lanes
+    case 0: return launch_frames_warps<16, 4>(warps, r, prm, io, B, stream, slots, tile);   // decoupled 4-joint fingers: block diagonal
+    case 1: return launch_frames_warps<16, 0>(warps, r, prm, io, B, stream, slots, tile);   // dense, 16 lanes
+    case 2: return launch_frames_warps<32, -1>(warps, r, prm, io, B, stream, slots, tile);  // trunk + decoupled fingers: arrow
+    default: return launch_frames_warps<32, 0>(warps, r, prm, io, B, stream, slots, tile);  // dense, 32 lanes
   }
 }
 
@@ -818,19 +825,64 @@ extern "C" int dexr_solve_frames_multi(const dexr_group_t* groups, int32_t num_g
   Side& sd = side[device];
   if (!sd.fork) CUDA_TRY(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(sd.fork, stream));
-  int gi = 0;
+  // Sizing the CTAs of all groups TOGETHER.  A CTA takes a whole SM (registers), so the CTAs of the concurrent kernels queue
+  // for SMs, and a CTA solves `round` = warps x frames-per-warp frames at a time.  A group that spreads over all SMs on its
+  // own (what a lone launch does) gives each CTA a thin tile that still costs whole rounds -- six robots x 2048 frames: 768
+  // CTAs, the 32-lane ones with 16 frames on 15 warps = two rounds, the second with one frame.  Instead, with
+  //   R = sum over groups of ceil(frames / round)   (CTA-rounds of work):
+  //   R <= SMs:      one wave; tiles shrunk by the common factor R / SMs so that every SM gets a CTA;
+  //   R < 8 SMs:     every CTA gets r = max(1, R / (4 SMs)) whole rounds and there are as many CTAs as that takes (about
+  //                  four waves; the hardware's CTA scheduler balances them over the SMs);
+  //   otherwise:     one persistent CTA per SM and group as in a lone launch (enough work per SM that the dynamic frame
+  //                  queue inside a CTA balances better than many short CTAs);
+  //   always:        groups are launched slowest solver first (32-lane dense, arrow, 16-lane dense, block diagonal), so the
+  //                  long CTAs are dispatched first and the short ones fill the tail.
+  // Measured on B200, six robots x n frames, ms per call (profiles/r02/mixed_sizing_sweep.txt), lone-launch sizing in the
+  // given order -> this: n = 512: 0.49 -> 0.21, 1024: 0.50 -> 0.31, 2048: 0.60 -> 0.52, 4096: 0.92 -> 0.86, 16 384: 2.77 -> 2.69.
+  // DEXR_MULTI_SLOTS=spread (read per call) restores the lone-launch sizing and the given order for A/B runs.
+  const char* slots_env = getenv("DEXR_MULTI_SLOTS");
+  const bool packed = !(slots_env && !strcmp(slots_env, "spread")) && m.n_groups > 1;
+  struct Plan { int group, kind, slots, tile; };
+  Plan plan[DEXR_MAX_GROUPS];
+  int n_plan = 0;
+  long long R = 0;
+  auto round_of = [](int kind) { return (frames_warps()[kind] - 1) * (kind <= 1 ? 2 : 1); };
   for (int i = 0; i < num_groups; ++i) {
-    const dexr_group_t& g = groups[i];
-    if (g.num_frames == 0) continue;
+    if (groups[i].num_frames == 0) continue;
+    const int k = solver_kind(groups[i].robot->host);
+    plan[n_plan++] = Plan{i, k, 0, 0};
+    R += (groups[i].num_frames + round_of(k) - 1) / round_of(k);
+  }
+  // tunables for A/B sweeps (read per call): CTA waves aimed at, and the work per SM (in rounds) from which every group goes
+  // back to one persistent CTA per SM
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; };
+  const int waves = env_int("DEXR_MULTI_WAVES", 4), spread_at = env_int("DEXR_MULTI_SPREAD_AT", 8);
+  if (packed && R < (long long)spread_at * sms) {
+    const long long r = std::max<long long>(1, R / ((long long)waves * sms));
+    for (int j = 0; j < n_plan; ++j) {
+      Plan& p = plan[j];
+      const long long B = groups[p.group].num_frames;
+      const int S = round_of(p.kind), max_tile = p.kind <= 1 ? FramesCfg<16>::kMaxTile : FramesCfg<32>::kMaxTile;
+      long long per = R <= sms ? std::max<long long>(1, (S * R + sms - 1) / sms) : r * S;  // frames per CTA
+      if (per <= max_tile) {                                 // one tile per CTA
+        p.tile = (int)(per > S ? (per & ~3LL) : per);  // one round: exactly the frames the warps hold (plain loads if not 4 | tile)
+        p.slots = (int)std::min<long long>((B + p.tile - 1) / p.tile, 1 << 20);
+      } else {
+        p.slots = (int)((B + per - 1) / per);
+      }
+    }
+  }
+  if (packed) std::stable_sort(plan, plan + n_plan, [](const Plan& x, const Plan& y) { return x.kind > y.kind; });
+  for (int gi = 0; gi < n_plan; ++gi) {
+    const dexr_group_t& g = groups[plan[gi].group];
     if (!sd.s[gi]) {
       CUDA_TRY(cudaStreamCreateWithFlags(&sd.s[gi], cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&sd.done[gi], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaStreamWaitEvent(sd.s[gi], sd.fork, 0));
-    if (int e = dexr_solve_frames(g.robot, g.params, &g.io, g.num_frames, sd.s[gi])) return e;
+    if (int e = launch_frames_kind(const_cast<dexr_robot*>(g.robot), g.params, &g.io, g.num_frames, sd.s[gi], plan[gi].slots, plan[gi].tile)) return e;
     CUDA_TRY(cudaEventRecord(sd.done[gi], sd.s[gi]));
     CUDA_TRY(cudaStreamWaitEvent(stream, sd.done[gi], 0));
-    ++gi;
   }
   return 0;
 }

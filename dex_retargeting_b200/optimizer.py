@@ -185,14 +185,14 @@ class Optimizer:
 
     def params(self, clip_init: bool = False, lp_alpha: float = -1.0, raw_hand=None) -> N.DexrParams:
         """`raw_hand`: None = the keypoints are wrist-centred MANO-convention points; HandType.right / left (or "right" /
-        "left") = they are RAW detector landmarks of that hand and the kernel pre-processes them itself (fused
+        "left", any case: single_hand_detector.py:47 spells them "Right" / "Left") = they are RAW detector landmarks of that hand and the kernel pre-processes them itself (fused
         single_hand_detector.py:100-103, 130-158)."""
         p = N.default_params()
         p.tol, p.lambda0, p.max_iters = self.step_tol, self.lambda0, int(self.max_iters)
         p.clip_init = 1 if clip_init else 0
         p.lp_alpha = float(lp_alpha)
         if raw_hand is not None:
-            name = raw_hand if isinstance(raw_hand, str) else raw_hand.name
+            name = (raw_hand if isinstance(raw_hand, str) else raw_hand.name).lower()  # the detector's own spelling is "Right" / "Left"
             if name not in ("right", "left"):
                 raise ValueError(f"raw_hand must be right or left, got {raw_hand!r}")
             p.preprocess = 1 if name == "right" else 2
@@ -372,11 +372,13 @@ class Optimizer:
 
 
 def retarget_batch_mixed(jobs, stream=None):
-    """Several robots, ONE launch (`dexr_solve_frames_multi`): `jobs` is a list of `(optimizer, kwargs)` where `kwargs` are the
+    """Several robots, ONE call (`dexr_solve_frames_multi`): `jobs` is a list of `(optimizer, kwargs)` where `kwargs` are the
     arguments of `Optimizer.retarget_batch` for that robot's batch (every optimizer on the same device, at most 16 groups).
-    The reference builds one optimizer per robot and would run them back to back (retargeting_config.py:167-257); here a CTA
-    walks the groups inside one persistent kernel, reloading the 8 KB robot table between groups, so small per-robot batches
-    do not each pay a launch and a tail.  Returns the list of result tensors, bit-identical to per-robot launches."""
+    The reference builds one optimizer per robot and would run them back to back (retargeting_config.py:167-257); here the
+    library forks one standalone persistent kernel per robot onto its own side streams and joins them on the caller's stream
+    with events, so the groups share the SMs and small per-robot batches do not each wait for the previous group's tail
+    (`DEXR_MULTI_MODE=persistent` selects the alternative, one kernel whose CTAs walk the groups; measured slower at every
+    size, profiles/r02/mixed_launch_sweep.txt).  Returns the list of result tensors, bit-identical to per-robot launches."""
     import torch
 
     if len(jobs) > N.MAX_GROUPS:

@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
-frames kernel (G=16 dense, G=16 block, G=32, mimic), sequences kernel, preprocessing kernel, ragged batch sizes."""
+frames kernel (G=16 dense, G=16 block, G=32 arrow / dense, mimic), fused preprocessing, sequences kernel (two half-warps per
+stream, one half-warp per stream, several streams per warp), the mixed-robot call (fork-join and persistent), the host-buffer
+call (pinned zero-copy and pageable staged), the preprocessing kernel, ragged batch sizes."""
+import os
 import sys
 from pathlib import Path
 
@@ -35,3 +38,52 @@ raw = torch.from_numpy(kp[:300].copy()).to(dev) + 0.1
 out = preprocess_keypoints(raw)
 torch.cuda.synchronize()
 print("preprocess ok", float(out.abs().sum()))
+
+# ---- round 2 additions -------------------------------------------------------------------------------------------------
+from dex_retargeting_b200.optimizer import retarget_batch_mixed  # noqa: E402
+
+seq = build_product("teleop/allegro_hand_right")
+opt = seq.optimizer
+B = 45
+rawk = torch.from_numpy(kp[:B].copy()).to(dev) + 0.05
+x0 = torch.from_numpy(np.tile(seq.joint_limits.mean(1).astype(np.float32), (B, 1))).to(dev)
+q = opt.retarget_batch(keypoints=rawk, last_qpos=x0, raw_hand="Right")
+torch.cuda.synchronize()
+print("fused preprocess ok", float(q.abs().sum()))
+
+seq = build_product("teleop/leap_hand_right_dexpilot")
+for duo, S, T in (("1", 5, 12), ("0", 5, 12), ("1", 148 * 8 + 37, 3)):
+    os.environ["DEXR_SEQ_DUO"] = duo
+    tk = torch.from_numpy(np.stack([kp[(7 * s) % 400:(7 * s) % 400 + T] for s in range(S)]).copy()).to(dev)
+    out, st = seq.retarget_sequences(tk)
+    torch.cuda.synchronize()
+    print(f"sequences duo={duo} S={S} ok", float(out.abs().sum()))
+os.environ.pop("DEXR_SEQ_DUO")
+
+for mode in ("streams", "persistent"):
+    os.environ["DEXR_MULTI_MODE"] = mode
+    jobs = []
+    for i, key in enumerate(("teleop/allegro_hand_right", "offline/shadow_hand_right", "teleop/leap_hand_right_dexpilot",
+                             "teleop/schunk_svh_hand_right")):
+        s_ = build_product(key)
+        o_ = s_.optimizer
+        n = 19 + 7 * i
+        job = dict(keypoints=torch.from_numpy(kp[i:i + n].copy()).to(dev),
+                   last_qpos=torch.from_numpy(np.tile(s_.joint_limits.mean(1).astype(np.float32), (n, 1))).to(dev), clip_init=True)
+        if o_.retargeting_type == "DEXPILOT":
+            job["projected"] = torch.zeros((n, o_._objective_spec().len_proj), dtype=torch.uint8, device=dev)
+        jobs.append((o_, job))
+    outs = retarget_batch_mixed(jobs)
+    torch.cuda.synchronize()
+    print(f"mixed {mode} ok", sum(float(o.abs().sum()) for o in outs))
+os.environ.pop("DEXR_MULTI_MODE")
+
+seq = build_product("teleop/allegro_hand_right")
+opt = seq.optimizer
+B = 300
+x0h = np.tile(seq.joint_limits.mean(1).astype(np.float32), (B, 1))
+o1 = opt.retarget_batch_host(keypoints=torch.from_numpy(kp[:B].copy()).pin_memory(), last_qpos=torch.from_numpy(x0h).pin_memory(),
+                             out=torch.empty((B, opt.opt_dof)).pin_memory())
+o2 = opt.retarget_batch_host(keypoints=kp[:B].copy(), last_qpos=x0h)
+torch.cuda.synchronize()
+print("host call ok", float(np.abs(np.asarray(o1) - np.asarray(o2)).max()))

@@ -28,6 +28,12 @@ if want ncu2; then
   ncu --set full --metrics "$M" --clock-control none --import-source on -k regex:dexr_ -s 1 -c 1 -f -o "$out/prof_streams_256x300" \
       python tools/profile_targets.py streams > "$out/ncu_streams.log" 2>&1
 fi
+if want sanitize; then
+  for tool in memcheck synccheck; do
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tests/tools/sanitize_run.py > "$out/sanitize_$tool.log" 2>&1
+    echo "$tool exit $?"; grep -E "ERROR SUMMARY|ok " "$out/sanitize_$tool.log" | tail -24
+  done
+fi
 du -sh "$out" 2>/dev/null
 if want dump; then
   python tests/tools/dump_status.py "$out/status_default.npz" 2>&1 | tee "$out/dump_default.log"
@@ -72,6 +78,9 @@ PY
 fi
 if want multisweep; then
   python tools/multi_sweep.py 2>&1 | tee "$out/multi_sweep.txt"
+fi
+if want multitune; then
+  python tools/multi_tune.py 2>&1 | tee "$out/multi_tune.txt"
 fi
 if want final; then
   # the record run: captures first, then the traffic file of THIS build, then the bench line that reads it
@@ -184,7 +193,7 @@ dev = torch.device("cuda", 0)
 tag = "prev" if os.environ.get("DEXR_LIBRARY") else "new "
 for key, seed, kw in ((W.SHADOW_POS_KEY, W.SHADOW_SEED, dict(narrow_dummy=True)), (W.METRIC_KEY, W.METRIC_SEED, {}), (W.LEAP_DEXPILOT_KEY, W.SHADOW_SEED, {})):
     seq = W.build(key, device=0)
-    for B in (2048, 8192, 16384, 32768):
+    for B in (int(x) for x in os.environ.get("DEXR_TILE_SIZES", "2048,8192,16384,32768").split(",")):
         kp, x0, f, _ = W.frames(seq, B, seed, **kw)
         k, x = torch.from_numpy(kp).to(dev), torch.from_numpy(x0).to(dev)
         out = torch.empty((B, seq.optimizer.opt_dof), dtype=torch.float32, device=dev)

@@ -21,7 +21,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     dev = torch.device("cuda", 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {}
-    for n in (64, 256, 1024, 4096, 16384):
+    for n in (64, 256, 1024, 2048, 4096, 16384):
         jobs = []
         for i, key in enumerate(W.MIXED_KEYS):
             seq = W.build(key, device=0)
@@ -33,12 +33,17 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         def mixed():
             retarget_batch_mixed(jobs)
 
+        def mixed_spread():
+            os.environ["DEXR_MULTI_SLOTS"] = "spread"
+            retarget_batch_mixed(jobs)
+            os.environ.pop("DEXR_MULTI_SLOTS")
+
         def sequential():
             for o, kw in jobs:
                 o.retarget_batch(**kw)
 
         res = {}
-        for name, fn in (("mixed", mixed), ("sequential", sequential)):
+        for name, fn in (("mixed", mixed), ("mixed_spread", mixed_spread), ("sequential", sequential)):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
@@ -53,7 +58,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     print(json.dumps(out))
 else:
     rows = {}
-    for mode in ("persistent", "streams", "auto"):
+    for mode in ("persistent", "streams"):
         env = dict(os.environ)
         if mode != "auto":
             env["DEXR_MULTI_MODE"] = mode
@@ -62,7 +67,7 @@ else:
             rows[mode] = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception:
             print(mode, "failed:", r.stderr[-500:])
-    print("frames/robot   persistent   streams      auto   one-after-the-other   (ms per six-robot step)")
-    for n in ("64", "256", "1024", "4096", "16384"):
-        p, s, a = (rows.get(m, {}).get(n, {}) for m in ("persistent", "streams", "auto"))
-        print(f"{int(n):12d}   {p.get('mixed', float('nan')):10.4f} {s.get('mixed', float('nan')):9.4f} {a.get('mixed', float('nan')):9.4f} {s.get('sequential', float('nan')):21.4f}")
+    print("frames/robot   persistent   fork-join packed (default)   fork-join spread   one-after-the-other   (ms per six-robot step)")
+    for n in ("64", "256", "1024", "2048", "4096", "16384"):
+        p, s = (rows.get(m, {}).get(n, {}) for m in ("persistent", "streams"))
+        print(f"{int(n):12d}   {p.get('mixed', float('nan')):10.4f} {s.get('mixed', float('nan')):28.4f} {s.get('mixed_spread', float('nan')):18.4f} {s.get('sequential', float('nan')):21.4f}")
