@@ -82,6 +82,13 @@ constexpr float kFarResidual = 1e30f; // (round 1 left the kinematic curvature o
                                      // from the targets; the positive-definite fallback now handles that case, and on targets out of reach
                                      // the term is what makes the iteration quadratic: 25-60 -> 4-8 iterations)
 constexpr float kTrustDecrease = 0.9f;  // a trusted step counts as progress when the gradient max-norm shrank below this factor
+// Stop one iteration ahead: the last iteration of a converging frame only confirms that its step is below the tolerance
+// (typical steps 5e-2, 4e-3, 1e-5, 2e-7 rad against tol = 1e-5).  When two consecutive first-trial steps contract by
+// rho = s_k / s_(k-1) the next one is at most rho s_k as long as the contraction does not get worse (it gets better:
+// the damping shrinks and Newton's rate is quadratic), so the frame ends after step k once s_k^2 / s_(k-1) < kStopAhead tol.
+constexpr float kStopAhead = 0.5f;
+constexpr float kStopAheadRate = 0.02f;  // contraction better than this per step is not extrapolated (a step right after a bound
+                                         // was released, or whose max-norm sits in a fast subspace, can look 100x better than the next)
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -666,6 +673,7 @@ struct Solver {
     // far out of reach), no creeping at a damping collected early (round 1: 583 of 614 400 DexPilot stream frames ran into
     // max_iters).  Two reverts in a row mean the KKT residual sits at its fp32 floor: the frame ends at the best point.
     float gn_prev = 0.f, x_prev = 0.f;
+    float s_prev = 0.f;  // the previous iteration's accepted step when that was a first-trial Newton step, else 0
     bool trust_prev = false;
     int stall = 0;
 
@@ -1221,6 +1229,10 @@ struct Solver {
 #pragma unroll
             for (int i = 0; i < 3; ++i) p[i] = pn[i];
             cur ^= 1;
+            // (see kStopAhead; not with active bounds, extra damping or the majoriser model in play)
+            const bool ahead = exact && !any_act && trial == 0 && !revert && lam <= prm.lambda0 &&
+                               step * fmaxf(step, kStopAheadRate * s_prev) < kStopAhead * prm.tol * s_prev;
+            s_prev = (trial == 0 && !revert) ? step : 0.f;
             if (verified) lam = fmaxf(lam * kLamDown, kLamMin);
             // fnoise is a worst-case bound (every rounding error with the same sign); a decrease beyond an eighth of it is
             // already unlikely to be noise: such a step is kept whatever the next gradient says (it just does not relax
@@ -1235,7 +1247,7 @@ struct Solver {
               ++rejects;
               if (stall >= 2) { done = true; status |= DEXR_STATUS_NOISEFLOOR; }
               revert = false;
-            } else if (step < prm.tol) {
+            } else if (step < prm.tol || ahead) {
               if (any_act) recheck = true;
               else done = true;
             }

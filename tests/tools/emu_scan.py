@@ -22,7 +22,7 @@ import workloads as W  # noqa: E402
 CASES = {"metric": (W.METRIC_KEY, W.METRIC_SEED, {}, "metric"), "cold": (W.METRIC_KEY, W.METRIC_SEED, dict(sigma=0.5), "metric_cold"),
          "shadow": (W.SHADOW_POS_KEY, W.SHADOW_SEED, dict(narrow_dummy=True), "shadow_narrow"),
          "shadowship": (W.SHADOW_POS_KEY, W.SHADOW_SEED, dict(narrow_dummy=False), "shadow_ship"),
-         "leapdp": (W.LEAP_DEXPILOT_KEY, W.SHADOW_SEED, {}, "leap_frames")}
+         "leapdp": (W.LEAP_DEXPILOT_KEY, W.SHADOW_SEED, {}, "leap_frames"), "real": (W.METRIC_KEY, 0, {}, "metric_real")}
 
 
 def _frames(args):
