@@ -54,7 +54,7 @@ class DexrFrames(C.Structure):
     _fields_ = [
         ("keypoints", C.c_void_p), ("ref_value", C.c_void_p), ("fixed_qpos", C.c_void_p), ("last_qpos", C.c_void_p),
         ("projected", C.c_void_p), ("qpos_out", C.c_void_p), ("robot_qpos_out", C.c_void_p),
-        ("status_out", C.c_void_p), ("cost_out", C.c_void_p),
+        ("status_out", C.c_void_p), ("cost_out", C.c_void_p), ("damping_io", C.c_void_p),
     ]
 
 
@@ -62,6 +62,7 @@ class DexrSequences(C.Structure):
     _fields_ = [
         ("keypoints", C.c_void_p), ("fixed_qpos", C.c_void_p), ("last_qpos", C.c_void_p), ("filter_state", C.c_void_p),
         ("filter_init", C.c_void_p), ("projected", C.c_void_p), ("robot_qpos_out", C.c_void_p), ("status_out", C.c_void_p),
+        ("damping_state", C.c_void_p),
     ]
 
 
@@ -80,7 +81,8 @@ class DexrLaunchInfo(C.Structure):
 
 
 EXPORTS = [
-    "dexr_version", "dexr_build_id", "dexr_last_error", "dexr_table_sizeof", "dexr_params_sizeof", "dexr_default_params",
+    "dexr_version", "dexr_build_id", "dexr_last_error", "dexr_table_sizeof", "dexr_params_sizeof", "dexr_frames_sizeof",
+    "dexr_sequences_sizeof", "dexr_default_params",
     "dexr_robot_create", "dexr_robot_create_from_device", "dexr_robot_device_table", "dexr_robot_destroy",
     "dexr_solve_frames", "dexr_solve_frames_multi", "dexr_solve_sequences", "dexr_solve_frames_host", "dexr_get_launch_info",
     "dexr_preprocess_keypoints",
@@ -134,6 +136,15 @@ def load():
         raise DexrError(f"dexr_table_t layout mismatch: library {lib.dexr_table_sizeof()} vs binding {C.sizeof(DexrTable)}")
     if lib.dexr_params_sizeof() != C.sizeof(DexrParams):
         raise DexrError("dexr_params_t layout mismatch between library and binding")
+    if hasattr(lib, "dexr_frames_sizeof"):
+        lib.dexr_frames_sizeof.restype = C.c_size_t
+        lib.dexr_sequences_sizeof.restype = C.c_size_t
+        if lib.dexr_frames_sizeof() != C.sizeof(DexrFrames) or lib.dexr_sequences_sizeof() != C.sizeof(DexrSequences):
+            raise DexrError("dexr_frames_t / dexr_sequences_t layout mismatch between library and binding (stale DEXR_LIBRARY?)")
+    elif not os.environ.get("DEXR_LIBRARY"):
+        raise DexrError(f"{path} does not export dexr_frames_sizeof: rebuild it (python -m dex_retargeting_b200.build --force)")
+    # (an older A/B library named by DEXR_LIBRARY reads a prefix of the buffer structs -- fields are only ever appended -- so
+    # the single-robot entry points still work with it; dexr_solve_frames_multi, whose groups embed the struct, does not)
     _LIB = lib
     return lib
 

@@ -148,6 +148,7 @@ __device__ __forceinline__ void frames_group(const FrameArgs& a, int first_tile)
         in.last = s_last + ci * a.dm.n_var;
         in.fixed = s_fixed + ci * a.dm.n_fixed;
         in.projected = a.io.projected ? a.io.projected + f * a.dm.len_proj : nullptr;
+        sv.lam_carry = a.io.damping_io ? a.io.damping_io[f] : 0.f;  // (every lane of the group reads the frame's word)
         const int status = sv.solve(in, active);
         if (active) {
           if (sv.var >= 0) a.io.qpos_out[f * a.dm.n_var + sv.var] = sv.x;
@@ -155,6 +156,7 @@ __device__ __forceinline__ void frames_group(const FrameArgs& a, int first_tile)
           if (sv.l == 0) {
             if (a.io.status_out) a.io.status_out[f] = status;
             if (a.io.cost_out) a.io.cost_out[f] = sv.F;
+            if (a.io.damping_io) a.io.damping_io[f] = sv.lam_carry;
           }
         }
       }
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
     if (active && sv.var >= 0) last = a.io.last_qpos[sc * a.dm.n_var + sv.var];
     if (active && use_filter && l < a.dm.dof) fy = a.io.filter_state[sc * a.dm.dof + l];
     if (active && use_filter) finit = a.io.filter_init[sc];
+    sv.lam_carry = (active && a.io.damping_state) ? a.io.damping_state[sc] : 0.f;  // then carried by solve() from frame to frame
     const float* kp_stream = a.io.keypoints + sc * a.steps * (3 * DEXR_NUM_KEYPOINTS);
     float pre[KPL];
 #pragma unroll
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dexr_sequences_kernel(const SeqArg
       if (sv.var >= 0) a.io.last_qpos[sc * a.dm.n_var + sv.var] = last;
       if (use_filter && l < a.dm.dof) a.io.filter_state[sc * a.dm.dof + l] = fy;
       if (use_filter && l == 0) a.io.filter_init[sc] = (uint8_t)finit;
+      if (a.io.damping_state && l == 0) a.io.damping_state[sc] = sv.lam_carry;
     }
   }
 }
@@ -551,6 +555,8 @@ const char* dexr_build_id(void) { return DEXR_BUILD_ID; }
 const char* dexr_last_error(void) { return g_err; }
 size_t dexr_table_sizeof(void) { return sizeof(dexr_table_t); }
 size_t dexr_params_sizeof(void) { return sizeof(dexr_params_t); }
+size_t dexr_frames_sizeof(void) { return sizeof(dexr_frames_t); }
+size_t dexr_sequences_sizeof(void) { return sizeof(dexr_sequences_t); }
 
 void dexr_default_params(dexr_params_t* p) {
   p->huber_delta = 0.02f;
@@ -1027,6 +1033,7 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
     map(h->robot_qpos_out, (const void**)&d.robot_qpos_out);
     map(h->status_out, (const void**)&d.status_out);
     map(h->cost_out, (const void**)&d.cost_out);
+    map(h->damping_io, (const void**)&d.damping_io);
     if (ok) {
       if (int e = dexr_solve_frames(robot, params, &d, B, robot->streams[0])) return e;
       CUDA_TRY(cudaStreamSynchronize(robot->streams[0]));
@@ -1036,14 +1043,14 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
   // per-frame device bytes, every sub-array padded so that chunk bases stay 16-byte aligned
   const size_t row_in = in_row * 4, row_last = t.n_var * 4, row_fixed = t.n_fixed * 4, row_proj = t.len_proj,
                row_q = t.n_var * 4, row_rq = h->robot_qpos_out ? t.dof * 4 : 0, row_st = h->status_out ? 4 : 0,
-               row_c = h->cost_out ? 4 : 0;
+               row_c = h->cost_out ? 4 : 0, row_dmp = h->damping_io ? 4 : 0;
   // chunks per call: enough to overlap copies with the solve, few enough that each launch still fills the GPU
   static const int n_chunks_env = [] { const char* e = getenv("DEXR_HOST_CHUNKS"); return e ? std::max(1, atoi(e)) : 0; }();
   const int n_chunks = n_chunks_env ? n_chunks_env : 4;
   const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, round_up((int)std::min<int64_t>((B + n_chunks - 1) / n_chunks, 1 << 20), 64)));
   auto pad = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t need = pad(chunk * row_in) + pad(chunk * row_last) + pad(chunk * row_fixed) + pad(chunk * row_proj) +
-                      pad(chunk * row_q) + pad(chunk * row_rq) + pad(chunk * row_st) + pad(chunk * row_c);
+                      pad(chunk * row_q) + pad(chunk * row_rq) + pad(chunk * row_st) + pad(chunk * row_c) + pad(chunk * row_dmp);
   for (int i = 0; i < 2; ++i)
     if (!robot->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&robot->streams[i], cudaStreamNonBlocking));
   if (robot->stage_bytes < need) {  // grow both staging buffers, or leave the handle with none (never a stale size)
@@ -1082,13 +1089,16 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
     float* d_rq = reinterpret_cast<float*>(take(chunk * row_rq));
     int32_t* d_st = reinterpret_cast<int32_t*>(take(chunk * row_st));
     float* d_c = reinterpret_cast<float*>(take(chunk * row_c));
+    float* d_dmp = reinterpret_cast<float*>(take(chunk * row_dmp));
     const float* h_in = h->keypoints ? h->keypoints : h->ref_value;
     CUDA_TRY(cudaMemcpyAsync(d_in, h_in + f0 * in_row, n * row_in, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_last, h->last_qpos + f0 * t.n_var, n * row_last, cudaMemcpyHostToDevice, s));
     if (t.n_fixed) CUDA_TRY(cudaMemcpyAsync(d_fixed, h->fixed_qpos + f0 * t.n_fixed, n * row_fixed, cudaMemcpyHostToDevice, s));
     const bool proj = h->projected && t.len_proj > 0;
     if (proj) CUDA_TRY(cudaMemcpyAsync(d_proj, h->projected + f0 * t.len_proj, n * row_proj, cudaMemcpyHostToDevice, s));
+    if (h->damping_io) CUDA_TRY(cudaMemcpyAsync(d_dmp, h->damping_io + f0, n * row_dmp, cudaMemcpyHostToDevice, s));
     dexr_frames_t d{};
+    d.damping_io = h->damping_io ? d_dmp : nullptr;
     d.keypoints = h->keypoints ? d_in : nullptr;
     d.ref_value = h->keypoints ? nullptr : d_in;
     d.last_qpos = d_last;
@@ -1103,6 +1113,7 @@ int dexr_solve_frames_host(dexr_robot_t* robot, const dexr_params_t* params, con
     if (h->robot_qpos_out) CUDA_TRY(cudaMemcpyAsync(h->robot_qpos_out + f0 * t.dof, d_rq, n * row_rq, cudaMemcpyDeviceToHost, s));
     if (h->status_out) CUDA_TRY(cudaMemcpyAsync(h->status_out + f0, d_st, n * row_st, cudaMemcpyDeviceToHost, s));
     if (h->cost_out) CUDA_TRY(cudaMemcpyAsync(h->cost_out + f0, d_c, n * row_c, cudaMemcpyDeviceToHost, s));
+    if (h->damping_io) CUDA_TRY(cudaMemcpyAsync(h->damping_io + f0, d_dmp, n * row_dmp, cudaMemcpyDeviceToHost, s));
     if (proj) CUDA_TRY(cudaMemcpyAsync(h->projected + f0 * t.len_proj, d_proj, n * row_proj, cudaMemcpyDeviceToHost, s));
     // the staging buffer of this stream is reused two chunks later: same stream => ordered
   }

@@ -138,15 +138,17 @@ class Optimizer:
         names = self.robot.dof_joint_names
         return [names[i] for i in self.idx_pin2fixed]
 
-    def retarget(self, ref_value, fixed_qpos, last_qpos):
+    def retarget(self, ref_value, fixed_qpos, last_qpos, damping=None):
         """One frame.  ref_value: (m,3); fixed_qpos: (len(idx_pin2fixed),); last_qpos: (opt_dof,) warm start
-        and regularisation anchor.  Returns float32 (opt_dof,) in `target_joint_names` order."""
+        and regularisation anchor.  Returns float32 (opt_dof,) in `target_joint_names` order.
+        `damping` (not in the reference): float32 array of one element that a caller feeding a STREAM frame by frame keeps
+        between calls -- the solver's carried damping (`dexr_frames_t.damping_io`), read and updated in place."""
         if len(fixed_qpos) != len(self.idx_pin2fixed):
             raise ValueError(
                 f"Optimizer has {len(self.idx_pin2fixed)} joints but non_target_qpos {fixed_qpos} is given"
             )
         qpos, _ = self._solve_host(np.asarray(ref_value, dtype=np.float32)[None], np.asarray(fixed_qpos, dtype=np.float32)[None],
-                                   np.asarray(last_qpos, dtype=np.float32)[None], clip_init=False)
+                                   np.asarray(last_qpos, dtype=np.float32)[None], clip_init=False, damping=damping)
         return qpos[0]
 
     # ---------------------------------------------------------------- engine
@@ -205,7 +207,7 @@ class Optimizer:
 
     # ---------------------------------------------------------------- host path (numpy, B small)
     def _solve_host(self, ref_value, fixed_qpos, last_qpos, clip_init, keypoints=None, projected=None,
-                    want_robot_qpos=False):
+                    want_robot_qpos=False, damping=None):
         eng = self.engine()
         B = last_qpos.shape[0]
         n = self.opt_dof
@@ -240,6 +242,10 @@ class Optimizer:
             io.robot_qpos_out = ptr(rq)
         if projected is not None:
             io.projected = ptr(projected)
+        if damping is not None:
+            if not isinstance(damping, np.ndarray) or damping.dtype != np.float32 or damping.shape != (B,) or not damping.flags.c_contiguous:
+                raise ValueError(f"damping must be a contiguous float32 array of shape ({B},) (updated in place)")
+            io.damping_io = ptr(damping)
         p = self.params(clip_init=clip_init)
         N.check(eng.lib.dexr_solve_frames_host(eng.handle, C.byref(p), C.byref(io), B), "dexr_solve_frames_host")
         # nlopt's last_optimum_value() is the reference objective's VALUE, which leaves the regulariser out
@@ -250,7 +256,7 @@ class Optimizer:
         return qpos, rq
 
     def retarget_batch_host(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
-                            out=None, clip_init=False, raw_hand=None):
+                            out=None, clip_init=False, raw_hand=None, damping=None):
         """Host-buffer twin of `retarget_batch`: float32 numpy arrays (or CPU torch tensors, ideally
         pinned) in, numpy out.  The library stages chunks through its own device buffers and overlaps the
         host->device copies, the solve and the device->host copies (`dexr_solve_frames_host`).  Returns
@@ -293,6 +299,11 @@ class Optimizer:
             if pj.dtype != np.uint8 or not pj.flags.c_contiguous:
                 raise ValueError("projected must be a contiguous uint8 array (updated in place)")
             io.projected = ptr(pj, (B, self._objective_spec().len_proj), "projected")
+        if damping is not None:  # per-frame carried damping of B streams fed frame by frame (dexr_frames_t.damping_io), in place
+            dm = damping.numpy() if hasattr(damping, "numpy") and not isinstance(damping, np.ndarray) else damping
+            if dm.dtype != np.float32 or not dm.flags.c_contiguous:
+                raise ValueError("damping must be a contiguous float32 array (updated in place)")
+            io.damping_io = ptr(dm, (B,), "damping")
         if out is None:
             out = np.empty((B, self.opt_dof), dtype=np.float32)
         out_np = out.numpy() if hasattr(out, "numpy") and not isinstance(out, np.ndarray) else out
@@ -305,26 +316,30 @@ class Optimizer:
 
     # ---------------------------------------------------------------- device path (torch, B large)
     def retarget_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None,
-                       out=None, robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None, raw_hand=None):
+                       out=None, robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None, raw_hand=None,
+                       damping=None):
         """Solve B independent frames in one launch.  All arguments are float32 CUDA tensors on this
         optimizer's device (projected: uint8, status_out: int32), contiguous:
           ref_value [B,m,3]  OR  keypoints [B,21,3] (the human-index gather is done in the kernel)
           fixed_qpos [B,len(idx_pin2fixed)] (omit when there are none), last_qpos [B,opt_dof]
         `raw_hand` (HandType): `keypoints` are raw detector landmarks of that hand; the wrist-frame estimate and the MANO
         rotation of the reference's detector are applied inside the solver (see `params`).
+        `damping` [B] float32, in/out: the carried damping of B STREAMS that are fed frame by frame through this call
+        (`StreamState.damping`, `dexr_frames_t.damping_io`); omit for independent frames.
         Returns qpos [B,opt_dof] (= `out` if given).  Nothing is synchronised."""
         import torch
 
         eng, io, p, out, B = self._prepare_batch(ref_value, fixed_qpos, last_qpos, keypoints=keypoints, projected=projected, out=out,
                                                  robot_qpos_out=robot_qpos_out, status_out=status_out, cost_out=cost_out,
-                                                 clip_init=clip_init, raw_hand=raw_hand)
+                                                 clip_init=clip_init, raw_hand=raw_hand, damping=damping)
         s = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", eng.device))
         N.check(eng.lib.dexr_solve_frames(eng.handle, C.byref(p), C.byref(io), B, C.c_void_p(s.cuda_stream)),
                 "dexr_solve_frames")
         return out
 
     def _prepare_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None, out=None,
-                       robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, raw_hand=None, stream=None):
+                       robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, raw_hand=None, stream=None,
+                       damping=None):
         """Validate the tensors of one batch and lay them out as `dexr_frames_t` (shared by the single-robot and the
         mixed-robot launch).  Returns (engine, io, params, out, B)."""
         import torch
@@ -366,6 +381,8 @@ class Optimizer:
             io.cost_out = chk(cost_out, (B,), torch.float32, "cost_out")
         if projected is not None:
             io.projected = chk(projected, (B, self._objective_spec().len_proj), torch.uint8, "projected")
+        if damping is not None:
+            io.damping_io = chk(damping, (B,), torch.float32, "damping")
         if raw_hand is not None and keypoints is None:
             raise ValueError("raw_hand needs `keypoints` (raw landmarks), not ref_value")
         return eng, io, self.params(clip_init=clip_init, raw_hand=raw_hand), out, B
@@ -533,13 +550,13 @@ class DexPilotOptimizer(Optimizer):
         p.huber_delta, p.norm_delta, p.scaling = self.huber_delta, self.norm_delta, self.scaling
         p.project_dist, p.escape_dist, p.eta1, p.eta2 = self.project_dist, self.escape_dist, self.eta1, self.eta2
 
-    def retarget(self, ref_value, fixed_qpos, last_qpos):
+    def retarget(self, ref_value, fixed_qpos, last_qpos, damping=None):
         if len(fixed_qpos) != len(self.idx_pin2fixed):
             raise ValueError(
                 f"Optimizer has {len(self.idx_pin2fixed)} joints but non_target_qpos {fixed_qpos} is given"
             )
         flags = np.ascontiguousarray(self.projected, dtype=np.uint8)[None]  # hysteresis state, updated in place
         qpos, _ = self._solve_host(np.asarray(ref_value, dtype=np.float32)[None], np.asarray(fixed_qpos, dtype=np.float32)[None],
-                                   np.asarray(last_qpos, dtype=np.float32)[None], clip_init=False, projected=flags)
+                                   np.asarray(last_qpos, dtype=np.float32)[None], clip_init=False, projected=flags, damping=damping)
         self.projected = flags[0].astype(bool)
         return qpos[0]

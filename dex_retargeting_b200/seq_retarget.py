@@ -33,6 +33,7 @@ class StreamState:
     filter_state: "torch.Tensor"  # [S, dof] float32
     filter_init: "torch.Tensor"   # [S] uint8
     projected: Optional["torch.Tensor"]  # [S, len_proj] uint8 (DexPilot) or None
+    damping: Optional["torch.Tensor"] = None  # [S] float32: the solver's carried damping (dexr_sequences_t.damping_state)
 
 
 def _quat_to_matrix(q):
@@ -74,6 +75,7 @@ class SeqRetargeting:
         self.joint_limits = joint_limits[optimizer.idx_pin2target]
 
         self.last_qpos = joint_limits.mean(1)[optimizer.idx_pin2target].astype(np.float32)
+        self._damping = np.zeros(1, dtype=np.float32)  # the stream's carried solver damping (Optimizer.retarget, `damping`)
         self.accumulated_time = 0
         self.num_retargeting = 0
         self.filter = lp_filter
@@ -157,6 +159,7 @@ class SeqRetargeting:
             ref_value=np.asarray(ref_value).astype(np.float32),
             fixed_qpos=np.asarray(fixed_qpos).astype(np.float32),
             last_qpos=np.clip(self.last_qpos, self.joint_limits[:, 0], self.joint_limits[:, 1]),
+            damping=self._damping,
         )
         self.accumulated_time += time.perf_counter() - tic
         self.num_retargeting += 1
@@ -172,6 +175,7 @@ class SeqRetargeting:
 
     def set_qpos(self, robot_qpos: np.ndarray):
         self.last_qpos = np.asarray(robot_qpos)[self.optimizer.idx_pin2target]
+        self._damping[:] = 0  # a new warm start: the solver's default damping again
 
     def get_qpos(self, fixed_qpos: Optional[np.ndarray] = None):
         robot_qpos = np.zeros(self.optimizer.robot.dof)
@@ -186,6 +190,7 @@ class SeqRetargeting:
 
     def reset(self):
         self.last_qpos = self.joint_limits.mean(1).astype(np.float32)
+        self._damping[:] = 0
         self.num_retargeting = 0
         self.accumulated_time = 0
 
@@ -212,6 +217,7 @@ class SeqRetargeting:
             filter_state=torch.zeros((num_streams, opt.robot.dof), dtype=torch.float32, device=dev),
             filter_init=torch.zeros((num_streams,), dtype=torch.uint8, device=dev),
             projected=torch.zeros((num_streams, len_proj), dtype=torch.uint8, device=dev) if len_proj else None,
+            damping=torch.zeros((num_streams,), dtype=torch.float32, device=dev),
         )
 
     def retarget_sequences(self, keypoints, state: Optional[StreamState] = None, fixed_qpos=None, out=None,
@@ -250,6 +256,8 @@ class SeqRetargeting:
         io.filter_init = chk(state.filter_init, (S,), torch.uint8, "state.filter_init")
         if state.projected is not None:
             io.projected = chk(state.projected, (S, state.projected.shape[1]), torch.uint8, "state.projected")
+        if state.damping is not None:
+            io.damping_state = chk(state.damping, (S,), torch.float32, "state.damping")
         if out is None:
             out = torch.empty((S, T, opt.robot.dof), dtype=torch.float32, device=dev)
         io.robot_qpos_out = chk(out, (S, T, opt.robot.dof), torch.float32, "out")

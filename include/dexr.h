@@ -167,6 +167,13 @@ typedef struct dexr_frames {
   float* robot_qpos_out;   /* [B,dof] or NULL: full qpos in pinocchio order, mimic applied          */
   int32_t* status_out;     /* [B] or NULL */
   float* cost_out;         /* [B] or NULL: final consistent objective value                         */
+  float* damping_io;       /* [B] or NULL.  Stream state for callers that feed a stream frame by frame (the reference's
+                            * teleoperation loop, one retarget() per camera frame): in = the Levenberg-Marquardt damping
+                            * this frame starts with (<= 0: params.lambda0), out = what the stream's NEXT frame should
+                            * start with (0.3 x the damping this frame's first accepted step needed, never below
+                            * params.lambda0).  NULL: every frame starts at params.lambda0.  The minimiser found is the
+                            * same; the state only saves the rejected steps a hard stretch of a trajectory would pay
+                            * again at the start of every frame.                                                        */
 } dexr_frames_t;
 
 /* Buffers of one batched sequence solve: S independent streams of T frames with
@@ -181,6 +188,8 @@ typedef struct dexr_sequences {
   uint8_t* projected;      /* [S,len_proj] in/out dexpilot flags, or NULL                           */
   float* robot_qpos_out;   /* [S,T,dof]  filtered full qpos, pinocchio order                        */
   int32_t* status_out;     /* [S,T] or NULL */
+  float* damping_state;    /* [S] in/out or NULL: the streams' carried damping (dexr_frames_t.damping_io); inside a call
+                            * it is carried in registers from frame to frame whether or not this array is given           */
 } dexr_sequences_t;
 
 typedef struct dexr_robot dexr_robot_t; /* opaque: device copy of the table + launch configuration */
@@ -197,6 +206,8 @@ const char* dexr_build_id(void);
 const char* dexr_last_error(void);
 size_t dexr_table_sizeof(void);
 size_t dexr_params_sizeof(void);
+size_t dexr_frames_sizeof(void);    /* sizeof(dexr_frames_t) / sizeof(dexr_sequences_t): a binding checks its mirror of the  */
+size_t dexr_sequences_sizeof(void); /* buffer structs against the library it loaded (dexr_group_t embeds dexr_frames_t)  */
 void dexr_default_params(dexr_params_t* p);
 
 /* Upload a host table to `device` (cudaMemcpy, synchronous; init time only). */

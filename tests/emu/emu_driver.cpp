@@ -96,7 +96,7 @@ struct Job {
   const float *kp, *ref, *last, *fixed;
   uint8_t* projected;
   long long B, base;
-  float *qpos_out, *robot_qpos_out, *cost_out;
+  float *qpos_out, *robot_qpos_out, *cost_out, *damping_io;
   int* status_out;
 } job;
 
@@ -115,8 +115,10 @@ void lane_body(int lane) {
   in.last = j.last + f * j.dm.n_var;
   in.fixed = j.fixed ? j.fixed + f * j.dm.n_fixed : nullptr;
   in.projected = j.projected ? j.projected + f * j.dm.len_proj : nullptr;
+  sv.lam_carry = j.damping_io ? j.damping_io[f] : 0.f;
   const int status = sv.solve(in, active);
   if (active) {
+    if (sv.l == 0 && j.damping_io) j.damping_io[f] = sv.lam_carry;
     if (sv.var >= 0) j.qpos_out[f * j.dm.n_var + sv.var] = sv.x;
     if (j.robot_qpos_out && sv.l < j.dm.dof) j.robot_qpos_out[f * j.dm.dof + sv.l] = sv.q;
     if (sv.l == 0) {
@@ -150,8 +152,8 @@ int run_all(char* err, int errlen) {
 // (arrow mode if the table qualifies and use_arrow).  Returns 0, or a negative code with a message in err.
 extern "C" int emu_solve_frames(const dexr_table_t* tb, const dexr_params_t* prm, int use_arrow, const float* keypoints,
                                 const float* ref_value, const float* last_qpos, const float* fixed_qpos, uint8_t* projected,
-                                long long B, float* qpos_out, float* robot_qpos_out, int* status_out, float* cost_out, char* err,
-                                int errlen) {
+                                long long B, float* qpos_out, float* robot_qpos_out, int* status_out, float* cost_out, float* damping_io,
+                                char* err, int errlen) {
   job = Job{};
   job.tb = tb; job.prm = *prm;
   Dims& d = job.dm;
@@ -160,6 +162,7 @@ extern "C" int emu_solve_frames(const dexr_table_t* tb, const dexr_params_t* prm
   d.len_s1 = tb->len_s1; d.block_width = tb->block_width; d.trunk = tb->arrow > 0 ? tb->arrow - 1 : 0;
   job.kp = keypoints; job.ref = ref_value; job.last = last_qpos; job.fixed = fixed_qpos; job.projected = projected;
   job.B = B; job.qpos_out = qpos_out; job.robot_qpos_out = robot_qpos_out; job.status_out = status_out; job.cost_out = cost_out;
+  job.damping_io = damping_io;
   if (tb->dof <= 16) return tb->block_width == 4 ? run_all<16, 4>(err, errlen) : run_all<16, 0>(err, errlen);
   if (tb->arrow > 0 && use_arrow) return run_all<32, -1>(err, errlen);
   return run_all<32, 0>(err, errlen);
@@ -198,6 +201,7 @@ void seq_lane_body(int lane) {
   if (active && sv.var >= 0) last = q.io.last_qpos[sc * j.dm.n_var + sv.var];
   if (active && use_filter && l < j.dm.dof) fy = q.io.filter_state[sc * j.dm.dof + l];
   if (active && use_filter) finit = q.io.filter_init[sc];
+  sv.lam_carry = (active && q.io.damping_state) ? q.io.damping_state[sc] : 0.f;
   for (int t = 0; t < q.T; ++t) {
     FrameInputs in;
     in.kp = q.io.keypoints + (sc * q.T + t) * 3 * DEXR_NUM_KEYPOINTS;
@@ -224,6 +228,7 @@ void seq_lane_body(int lane) {
     if (sv.var >= 0) q.io.last_qpos[sc * j.dm.n_var + sv.var] = last;
     if (use_filter && l < j.dm.dof) q.io.filter_state[sc * j.dm.dof + l] = fy;
     if (use_filter && l == 0) q.io.filter_init[sc] = (uint8_t)finit;
+    if (q.io.damping_state && l == 0) q.io.damping_state[sc] = sv.lam_carry;
   }
 }
 

@@ -36,9 +36,9 @@ def load(defines: tuple = ()):
 
 
 def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None, projected=None, defines=(), use_arrow=True,
-                 clip_init=False, want_robot_qpos=False, raw_hand=None):
+                 clip_init=False, want_robot_qpos=False, raw_hand=None, damping=None):
     """Emulated dexr_solve_frames for an Optimizer of the host mirror.  Returns (qpos [B,n], status [B], cost [B])
-    (+ the full joint vector [B,dof] with want_robot_qpos)."""
+    (+ the full joint vector [B,dof] with want_robot_qpos).  `damping`: float32 [B] in/out (dexr_frames_t.damping_io)."""
     from dex_retargeting_b200 import _native as N
 
     lib = load(tuple(defines))
@@ -60,7 +60,7 @@ def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None
 
     full = np.zeros((B, table.dof), np.float32) if want_robot_qpos else None
     rc = lib.emu_solve_frames(C.byref(table), C.byref(prm), C.c_int(int(use_arrow)), ptr(kp), ptr(ref), ptr(last), ptr(fixed),
-                              ptr(projected), C.c_longlong(B), ptr(out), ptr(full), ptr(status), ptr(cost), err, C.c_int(600))
+                              ptr(projected), C.c_longlong(B), ptr(out), ptr(full), ptr(status), ptr(cost), ptr(damping), err, C.c_int(600))
     if rc != 0:
         raise RuntimeError(f"host emulation failed ({rc}): {err.value.decode()}")
     return (out, status, cost, full) if want_robot_qpos else (out, status, cost)
@@ -68,7 +68,7 @@ def solve_frames(opt, last_qpos, keypoints=None, ref_value=None, fixed_qpos=None
 
 def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_hand=None, duo=False):
     """Emulated dexr_solve_sequences for a SeqRetargeting of the host mirror: keypoints [S,T,21,3] -> filtered robot qpos
-    [S,T,dof]; `state` = dict(last_qpos, filter_state, filter_init, projected) carried between calls (created if None).
+    [S,T,dof]; `state` = dict(last_qpos, filter_state, filter_init, projected, damping) carried between calls (created if None).
     `duo`: the scarce-streams mode of the 16-lane solver (both half-warps on one stream, residual passes split)."""
     from dex_retargeting_b200 import _native as N
 
@@ -81,7 +81,8 @@ def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_
     if state is None:  # SeqRetargeting.make_stream_state: mid-range warm start, filter not initialised, no projection
         state = dict(last_qpos=np.tile(seq.joint_limits.mean(1).astype(np.float32), (S, 1)),
                      filter_state=np.zeros((S, table.dof), np.float32), filter_init=np.zeros(S, np.uint8),
-                     projected=np.zeros((S, table.len_proj), np.uint8) if opt.retargeting_type == "DEXPILOT" else None)
+                     projected=np.zeros((S, table.len_proj), np.uint8) if opt.retargeting_type == "DEXPILOT" else None,
+                     damping=np.zeros(S, np.float32))
     out = np.full((S, T, table.dof), np.nan, np.float32)
     status = np.zeros((S, T), np.int32)
     io = N.DexrSequences()
@@ -89,6 +90,8 @@ def solve_sequences(seq, keypoints, state=None, defines=(), use_arrow=True, raw_
     io.filter_state, io.filter_init = state["filter_state"].ctypes.data, state["filter_init"].ctypes.data
     io.projected = state["projected"].ctypes.data if state["projected"] is not None else None
     io.robot_qpos_out, io.status_out = out.ctypes.data, status.ctypes.data
+    if state.get("damping") is not None:
+        io.damping_state = state["damping"].ctypes.data
     err = C.create_string_buffer(600)
     lib.emu_solve_sequences.restype = C.c_int
     rc = lib.emu_solve_sequences(C.byref(table), C.byref(prm), C.c_int(int(use_arrow)), C.byref(io), C.c_longlong(S),

@@ -30,6 +30,8 @@ def test_struct_layouts():
     assert lib.dexr_version() == 1
     assert lib.dexr_table_sizeof() == C.sizeof(N.DexrTable) == 8192
     assert lib.dexr_params_sizeof() == C.sizeof(N.DexrParams) == 52
+    assert lib.dexr_frames_sizeof() == C.sizeof(N.DexrFrames) == 80
+    assert lib.dexr_sequences_sizeof() == C.sizeof(N.DexrSequences) == 72
     p = N.default_params()
     assert (p.huber_delta, p.norm_delta, p.max_iters, p.clip_init) == (pytest.approx(0.02), pytest.approx(4e-3), 64, 0)
     assert p.tol == pytest.approx(1e-5) and p.lambda0 == pytest.approx(1e-2) and p.lp_alpha < 0

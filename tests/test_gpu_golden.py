@@ -33,7 +33,9 @@ def test_frames_against_golden(case):
     assert same.mean() >= 0.9, f"{case}: {same.mean():.2f} within {TOL}, worst {dq.max():.2e}"
     assert np.median(dq) < 1e-5
     fb = VEC[f"{case}/cost_converged"]
-    np.testing.assert_allclose(cost[same], fb[same], rtol=3e-5, atol=1e-8)
+    # the kernel reports F in fp32: link positions of ~1 m carry ~6e-8 m of rounding, a 5 mm residual therefore ~1e-5 relative
+    # and F (quadratic in the residuals) ~2e-5 per term -- measured spread on the dummy-base hands +-2.6e-5, outliers 7e-5
+    np.testing.assert_allclose(cost[same], fb[same], rtol=1.5e-4, atol=1e-8)
 
 
 def test_stream_against_golden():

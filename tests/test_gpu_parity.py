@@ -244,6 +244,7 @@ def test_single_frame_api_matches_batch_and_oracle():
         last = seq.joint_limits.mean(1).astype(np.float32)
         proj = (torch.zeros((1, opt._objective_spec().len_proj), dtype=torch.uint8, device=dev)
                 if opt.retargeting_type == "DEXPILOT" else None)
+        dmp = torch.zeros((1,), dtype=torch.float32, device=dev)  # the stream's carried damping, as SeqRetargeting keeps it
         y = None
         for f in range(0, 60, 6):
             ref = o.ref_from_keypoints(kp[f])
@@ -254,10 +255,11 @@ def test_single_frame_api_matches_batch_and_oracle():
             lastc = np.clip(last, seq.joint_limits[:, 0], seq.joint_limits[:, 1]).astype(np.float32)
             rq = torch.zeros((1, opt.robot.dof), dtype=torch.float32, device=dev)
             q = twin.retarget_batch(torch.from_numpy(ref.astype(np.float32)[None]).to(dev), None,
-                                    torch.from_numpy(lastc[None]).to(dev), robot_qpos_out=rq, projected=proj)
+                                    torch.from_numpy(lastc[None]).to(dev), robot_qpos_out=rq, projected=proj, damping=dmp)
             torch.cuda.synchronize()
             last = q.cpu().numpy()[0]
             np.testing.assert_array_equal(seq.last_qpos, last)
+            np.testing.assert_array_equal(seq._damping, dmp.cpu().numpy())  # host path (staged copy in and out) == device path
             full = rq.cpu().numpy()[0].astype(np.float64)
             y = full if y is None else y + seq.filter.alpha * (full - y)
             np.testing.assert_allclose(a, y, atol=1e-6)
@@ -333,12 +335,13 @@ def test_sequences_kernel_matches_sequential_oracle(monkeypatch):
         for t in range(T):
             rq = torch.zeros((S, opt.robot.dof), dtype=torch.float32, device=dev)
             q = opt.retarget_batch(keypoints=tk[:, t].contiguous(), last_qpos=st.last_qpos, robot_qpos_out=rq,
-                                   projected=st.projected, clip_init=True)
+                                   projected=st.projected, clip_init=True, damping=st.damping)  # the stream's carried damping
             st.last_qpos = q
             y = rq if y is None else y + seq.filter.alpha * (rq - y)
             torch.cuda.synchronize()
             np.testing.assert_allclose(got[:, t], y.cpu().numpy(), atol=2e-6, err_msg=f"{key} step {t}")
         np.testing.assert_array_equal(state.last_qpos.cpu().numpy(), st.last_qpos.cpu().numpy())
+        np.testing.assert_array_equal(state.damping.cpu().numpy(), st.damping.cpu().numpy())
         if st.projected is not None:
             np.testing.assert_array_equal(state.projected.cpu().numpy(), st.projected.cpu().numpy())
         # (2) oracle recurrence

@@ -135,9 +135,10 @@ def test_streams_recurrence(key, vs_oracle):
     # frame-by-frame twin
     last = np.tile(seq.joint_limits.mean(1).astype(np.float32), (S, 1))
     proj = np.zeros((S, opt._objective_spec().len_proj), np.uint8) if opt.retargeting_type == "DEXPILOT" else None
+    damping = np.zeros(S, np.float32)  # the streams' carried damping (dexr_frames_t.damping_io), updated in place
     y = None
     for t in range(T):
-        q, _, _ = emu_host.solve_frames(opt, last, keypoints=kps[:, t], projected=proj, clip_init=True)
+        q, _, _ = emu_host.solve_frames(opt, last, keypoints=kps[:, t], projected=proj, clip_init=True, damping=damping)
         last = q
         full = np.zeros((S, opt.robot.dof), np.float32)
         full[:, opt.idx_pin2target] = q
@@ -146,6 +147,8 @@ def test_streams_recurrence(key, vs_oracle):
         y = full if y is None else y + np.float32(seq.low_pass_alpha) * (full - y)
         np.testing.assert_allclose(got[:, t], y, atol=2e-6, err_msg=f"{key} step {t}")
     np.testing.assert_array_equal(state["last_qpos"], last)
+    np.testing.assert_array_equal(state["damping"], damping)
+    assert np.all(damping >= np.float32(opt.lambda0))
     if proj is not None:
         np.testing.assert_array_equal(state["projected"], proj)
     if vs_oracle:

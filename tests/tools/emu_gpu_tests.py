@@ -74,13 +74,14 @@ def use_arrow():
 
 
 def retarget_batch(self, ref_value=None, fixed_qpos=None, last_qpos=None, *, keypoints=None, projected=None, out=None,
-                   robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None):
+                   robot_qpos_out=None, status_out=None, cost_out=None, clip_init=False, stream=None, damping=None):
     B = last_qpos.shape[0]
     if B == 0:
         return real_torch.empty((0, self.opt_dof)) if out is None else out
     q, status, cost, full = emu_host.solve_frames(self, _np(last_qpos), keypoints=_np(keypoints), ref_value=_np(ref_value),
                                                  fixed_qpos=_np(fixed_qpos), projected=_np(projected), defines=DEFINES,
-                                                 use_arrow=use_arrow(), clip_init=clip_init, want_robot_qpos=True)
+                                                 use_arrow=use_arrow(), clip_init=clip_init, want_robot_qpos=True,
+                                                 damping=_np(damping))  # (in place: the tensor shares its memory with the array)
     for dst, src in ((status_out, status), (cost_out, cost), (robot_qpos_out, full)):
         if dst is not None:
             dst.copy_(real_torch.from_numpy(src))
@@ -95,14 +96,15 @@ def make_stream_state(self, num_streams):
     lp = opt._objective_spec().len_proj
     return StreamState(last_qpos=real_torch.from_numpy(np.tile(self.joint_limits.mean(1).astype(np.float32), (num_streams, 1))),
                        filter_state=real_torch.zeros((num_streams, opt.robot.dof)), filter_init=real_torch.zeros(num_streams, dtype=real_torch.uint8),
-                       projected=real_torch.zeros((num_streams, lp), dtype=real_torch.uint8) if lp else None)
+                       projected=real_torch.zeros((num_streams, lp), dtype=real_torch.uint8) if lp else None,
+                       damping=real_torch.zeros(num_streams))
 
 
 def retarget_sequences(self, keypoints, state=None, fixed_qpos=None, out=None, status_out=None, stream=None):
     S = keypoints.shape[0]
     state = state if state is not None else self.make_stream_state(S)
     st = dict(last_qpos=_np(state.last_qpos), filter_state=_np(state.filter_state), filter_init=_np(state.filter_init),
-              projected=_np(state.projected))
+              projected=_np(state.projected), damping=_np(state.damping))
     got, status, _ = emu_host.solve_sequences(self, _np(keypoints), state=st, defines=DEFINES, use_arrow=use_arrow())
     if status_out is not None:
         status_out.copy_(real_torch.from_numpy(status))
@@ -110,6 +112,16 @@ def retarget_sequences(self, keypoints, state=None, fixed_qpos=None, out=None, s
         out.copy_(real_torch.from_numpy(got))
         return out, state
     return real_torch.from_numpy(got), state
+
+
+class EnvPatch:
+    """Stand-in for pytest's monkeypatch (setenv / delenv only; the emulated entry points ignore the library's switches)."""
+
+    def setenv(self, k, v):
+        os.environ[k] = v
+
+    def delenv(self, k, raising=True):
+        os.environ.pop(k, None)
 
 
 def expand(fn):
@@ -146,6 +158,8 @@ def main():
                     continue
                 if "tmp_path" in fn.__code__.co_varnames[:fn.__code__.co_argcount]:
                     kw = dict(kw, tmp_path=Path(tempfile.mkdtemp()))
+                if "monkeypatch" in fn.__code__.co_varnames[:fn.__code__.co_argcount]:
+                    kw = dict(kw, monkeypatch=EnvPatch())
                 t0 = time.time()
                 ran += 1
                 try:
