@@ -107,7 +107,7 @@ class Optimizer:
         self.max_iters = 64
         # DEXR_STEP_TOL overrides the default stopping step for A/B runs; the attribute stays settable
         self.step_tol = float(os.environ.get("DEXR_STEP_TOL", 1e-5))
-        self.lambda0 = 1e-2
+        self.lambda0 = float(os.environ.get("DEXR_LAMBDA0", 1e-2))
 
     # ---------------------------------------------------------------- reference API
     def set_joint_limit(self, joint_limits: np.ndarray, epsilon=1e-3):
