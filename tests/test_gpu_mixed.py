@@ -43,14 +43,19 @@ def _clone(kw):
     ([W.LEAP_DEXPILOT_KEY, W.SHADOW_POS_KEY, "offline/schunk_svh_hand_right", W.METRIC_KEY, "teleop/panda_gripper"],
      [500, 300, 200, 4096, 50]),                                                        # dexpilot flags, free-flying bases, prismatic
     ([W.METRIC_KEY], [5000]),                                                           # a single group
-], ids=["six-robots", "ragged", "loss-families", "single"])
-@pytest.mark.parametrize("mode", ["streams", "persistent"])
+    (W.MIXED_KEYS, [9000] * 6),                                                         # enough work per SM: one persistent CTA per SM and group
+], ids=["six-robots", "ragged", "loss-families", "single", "six-robots-large"])
+@pytest.mark.parametrize("mode", ["streams", "streams-spread", "persistent"])
 def test_mixed_launch_equals_per_robot_launches(keys, sizes, mode, monkeypatch):
-    """Both implementations behind dexr_solve_frames_multi: fork-join launches on side streams (default) and the single
-    persistent kernel whose CTAs walk the groups (DEXR_MULTI_MODE=persistent, read per call)."""
+    """Every implementation behind dexr_solve_frames_multi: fork-join launches on side streams with the CTAs of all groups
+    sized together (default: one-round tiles of exact size, shrunk tiles, whole-round CTAs or persistent CTAs depending on
+    the total work, slowest solver first), the same with every group sized as a lone launch (DEXR_MULTI_SLOTS=spread), and
+    the single persistent kernel whose CTAs walk the groups (DEXR_MULTI_MODE=persistent); all switches are read per call."""
     import torch
 
-    monkeypatch.setenv("DEXR_MULTI_MODE", mode)
+    monkeypatch.setenv("DEXR_MULTI_MODE", "persistent" if mode == "persistent" else "streams")
+    if mode == "streams-spread":
+        monkeypatch.setenv("DEXR_MULTI_SLOTS", "spread")
 
     from dex_retargeting_b200.optimizer import retarget_batch_mixed
 

