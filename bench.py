@@ -15,7 +15,9 @@ Workloads are generated on the host by tools/workloads.py (seeded numpy: q* ~ U(
 One JSON line on stdout (rank 0):
   value      device-timed throughput of the headline, inputs resident in HBM, CUDA events, max over ranks
   e2e        the same batch through the host-buffer C-ABI call (pinned host memory in and out, copies inside the timed region);
-             `e2e.staged_pageable` = the same call on pageable numpy buffers (chunked H2D -> solve -> D2H pipeline)
+             `e2e.staged_pageable` = the same call on pageable numpy buffers (chunked H2D -> solve -> D2H pipeline);
+             `e2e.ref_value_form` = the same call fed ref_value [B,m,3], the form Optimizer.retarget receives (secondary: the
+             headline form is the 21 keypoints north_star names)
   roofline   algorithmic HBM bytes / measured launch time vs the measured copy peak (the contract figure), plus what
              actually bounds the solver: `issue` (warp instructions per second vs 4 issue slots x SMs x clock) and `fp32`
              (executed FP32 operations per second vs 2 x 128 lanes x SMs x clock), both from the committed ncu capture of the
