@@ -879,18 +879,23 @@ extern "C" int dexr_solve_frames_multi(const dexr_group_t* groups, int32_t num_g
     }
   }
   if (packed) std::stable_sort(plan, plan + n_plan, [](const Plan& x, const Plan& y) { return x.kind > y.kind; });
-  for (int gi = 0; gi < n_plan; ++gi) {
+  // A failure in the middle must not leave kernels of this call running behind the caller's stream: every side stream that
+  // was forked is joined whatever happens after it, and the first error is reported at the end.
+  int rc = 0;
+  for (int gi = 0; gi < n_plan && rc == 0; ++gi) {
     const dexr_group_t& g = groups[plan[gi].group];
     if (!sd.s[gi]) {
       CUDA_TRY(cudaStreamCreateWithFlags(&sd.s[gi], cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&sd.done[gi], cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaStreamWaitEvent(sd.s[gi], sd.fork, 0));
-    if (int e = launch_frames_kind(const_cast<dexr_robot*>(g.robot), g.params, &g.io, g.num_frames, sd.s[gi], plan[gi].slots, plan[gi].tile)) return e;
-    CUDA_TRY(cudaEventRecord(sd.done[gi], sd.s[gi]));
-    CUDA_TRY(cudaStreamWaitEvent(stream, sd.done[gi], 0));
+    cudaError_t ce = cudaStreamWaitEvent(sd.s[gi], sd.fork, 0);
+    if (ce == cudaSuccess)
+      rc = launch_frames_kind(const_cast<dexr_robot*>(g.robot), g.params, &g.io, g.num_frames, sd.s[gi], plan[gi].slots, plan[gi].tile);
+    if (ce == cudaSuccess) ce = cudaEventRecord(sd.done[gi], sd.s[gi]);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(stream, sd.done[gi], 0);
+    if (ce != cudaSuccess && rc == 0) rc = fail(DEXR_E_CUDA, "dexr_solve_frames_multi: group %d: %s", plan[gi].group, cudaGetErrorString(ce));
   }
-  return 0;
+  return rc;
 }
 
 extern "C" int dexr_solve_frames(const dexr_robot_t* robot, const dexr_params_t* params, const dexr_frames_t* io,
