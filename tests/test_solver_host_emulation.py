@@ -280,3 +280,58 @@ def test_two_half_warps_on_one_stream_match_the_single_group(key):
     assert np.median(d) < 1e-6 and (d < 1e-4).mean() > 0.97, (np.median(d), d.max())
     if st_a["projected"] is not None:
         np.testing.assert_array_equal(st_a["projected"], st_b["projected"])
+
+
+def test_stop_one_iteration_ahead_stays_inside_the_step_tolerance():
+    """kStopAhead (dexr_kernels.cuh): a frame whose last two first-trial steps contract fast enough ends without the iteration
+    that would only confirm it.  On the first 512 frames bench.py times that must (a) save iterations -- the round-2 solver
+    before it took 3.21 per frame -- and (b) leave every frame within the step tolerance (1e-5 rad) of the oracle's converged
+    minimiser, ten times inside the parity bar."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import parity as P
+    import workloads as W
+
+    seq = W.build(W.METRIC_KEY)
+    kp, x0, _, _ = W.frames(seq, 65536, W.METRIC_SEED)
+    n = 512
+    q, st, _ = emu_host.solve_frames(seq.optimizer, x0[:n], keypoints=kp[:n])
+    assert np.all((st >> 24) == 0)
+    it = st & 0xffff
+    assert it.mean() < 2.7, it.mean()
+    dq = np.abs(q - P.fixture()["metric/q"][:n]).max(1)
+    assert dq.max() < 1e-5 and np.median(dq) < 5e-7, (dq.max(), np.median(dq))
+
+
+def test_a_stream_carries_its_damping():
+    """kCarry: fed frame by frame, a stream that hands the solver's damping from one frame to the next (damping_io) pays fewer
+    rejected steps than the same stream with every frame starting at lambda0, and ends at the same joint angles wherever both
+    stay in one basin; the carried value never drops below lambda0."""
+    seq = build_product("teleop/leap_hand_right_dexpilot")
+    opt = seq.optimizer
+    kp = keypoint_trajectory()[:120].astype(np.float32)
+    S = 1
+
+    def run(carry):
+        last = np.tile(seq.joint_limits.mean(1).astype(np.float32), (S, 1))
+        proj = np.zeros((S, opt._objective_spec().len_proj), np.uint8)
+        damping = np.zeros(S, np.float32) if carry else None
+        rejects, out, seen = 0, [], []
+        for t in range(kp.shape[0]):
+            q, st, _ = emu_host.solve_frames(opt, last, keypoints=kp[t][None], projected=proj, clip_init=True, damping=damping)
+            assert (st >> 24) == 0
+            rejects += int((st[0] >> 16) & 0x7f)
+            last = q
+            out.append(q[0].copy())
+            if carry:
+                seen.append(float(damping[0]))
+        return rejects, np.array(out), seen
+
+    r_carry, q_carry, seen = run(True)
+    r_plain, q_plain, _ = run(False)
+    assert min(seen) >= np.float32(opt.lambda0) and max(seen) > np.float32(opt.lambda0)  # some stretch needed more damping
+    assert r_carry <= r_plain, (r_carry, r_plain)
+    same = np.abs(q_carry - q_plain).max(1) < TOL
+    assert same.mean() > 0.5, same.mean()
