@@ -107,6 +107,8 @@ class Optimizer:
         self.max_iters = 64
         # DEXR_STEP_TOL overrides the default stopping step for A/B runs; the attribute stays settable
         self.step_tol = float(os.environ.get("DEXR_STEP_TOL", 1e-5))
+        # initial Levenberg-Marquardt damping: 1e-2, and 1.0 once a mimic adaptor is set (set_kinematic_adaptor); DEXR_LAMBDA0
+        # overrides both for A/B runs; the attribute stays settable
         self.lambda0 = float(os.environ.get("DEXR_LAMBDA0", 1e-2))
 
     # ---------------------------------------------------------------- reference API
@@ -132,6 +134,14 @@ class Optimizer:
         mimic = set(int(i) for i in adaptor.idx_pin2mimic)  # mimic joints are driven, not supplied
         self.idx_pin2fixed = np.array([x for x in self.idx_pin2fixed if int(x) not in mimic], dtype=int)
         self._engine = None
+        # Robots with mimic joints fold the kinematic curvature into the reduced Hessian (H_x = M^T H_q M), where the solver's
+        # positive-definite fallback cannot take it out again: an indefinite Hessian is only cured by more damping, one
+        # factor 10 per failed factorisation.  Measured on 512 seeded frames per hand (host emulation, warm start 0.05 rad):
+        # teleop SVH / Inspire / Ability pay 3.3 / 4.6 / 4.0 rejected trials per frame from 1e-2 and 1.5 / 2.7 / 2.1 from 1.0,
+        # at unchanged iteration counts and identical answers; 10 is better still for the vector hands but costs the position
+        # configurations iterations (offline Inspire 5.85 -> 6.36).
+        if "DEXR_LAMBDA0" not in os.environ and len(mimic) > 0:
+            self.lambda0 = 1.0
 
     @property
     def fixed_joint_names(self):
