@@ -1,6 +1,9 @@
 #!/usr/bin/env bash
 # One gpurun call: GPU suite, bench line, launch list + full ncu captures, status dumps.  Writes gpurun_out/job/.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_job.sh [suite] [bench] [ncu] [ncu2] [dump] [dumpvar]'
+#   gpurun --timeout 1500 -- 'bash tools/gpu_job.sh [suite] [bench] [final] [sanitize] [multisweep] [multitune] [streams256] [tiles] [abprev] ...'
+# `final` = the record run (captures, traffic file of this build, bench line, reference arm); then `python tools/collect_profiles.py`.
+# `abprev` / `tiles` / `ncuab` / `g16d` / `warps` compare against dex_retargeting_b200/variants/libdexr_prev.so (a library built from the
+# previous commit's sources; single-robot entry points only, see _native.py).
 set -u
 out=gpurun_out/job
 mkdir -p "$out"
@@ -37,25 +40,6 @@ fi
 du -sh "$out" 2>/dev/null
 if want dump; then
   python tests/tools/dump_status.py "$out/status_default.npz" 2>&1 | tee "$out/dump_default.log"
-fi
-if want dumpvar; then
-  DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_pdfallback_fknoise.so python tests/tools/dump_status.py "$out/status_pdfallback_fknoise.npz" 2>&1 | tee "$out/dump_pdfallback_fknoise.log"
-  DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_fknoise.so python tests/tools/dump_status.py "$out/status_fknoise.npz" 2>&1 | tee "$out/dump_fknoise.log"
-fi
-if want mixedab; then
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_default.json" 2> "$out/bench_default.err"
-  DEXR_LIBRARY=$PWD/dex_retargeting_b200/variants/libdexr_multi_calls.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_multi_calls.json" 2> "$out/bench_multi_calls.err"
-  DEXR_SEQ_PAIR=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_seq_pair.json" 2> "$out/bench_seq_pair.err"
-  python - <<'PY'
-import json
-for n in ("default", "multi_calls", "seq_pair"):
-    try:
-        d = json.loads(open(f"gpurun_out/job/bench_{n}.json").read().strip().splitlines()[-1])
-        c = {r["name"]: r for r in d["configs"]}
-        print(f"{n:12s} headline {d['value']:.4e}  mixed {c['mixed_robots']['ms_per_step']:.3f} ms (six launches {c['mixed_robots'].get('six_launches_ms_this_rank', 0):.3f})  streams {c['leap_dexpilot_streams']['ms_per_step']:.3f} ms")
-    except Exception as e:
-        print(n, "FAILED", e)
-PY
 fi
 if want streams256; then
   python - <<'PY'
