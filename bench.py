@@ -567,12 +567,19 @@ def main():
             if not captures:
                 cap_note = f"profiles/roofline_traffic.json was captured from another library build (loaded build {build_id}): traffic / issue / fp32 withheld"
 
-        def roof(name, frames_per_launch, ms, bpf):
+        def roof(name, frames_per_launch, ms, bpf, iters=None):
             ach = bpf * frames_per_launch / (ms * 1e-3) / 1e9
             r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                  "peak_source": peak_src, "bytes_per_frame": bpf, "launch_ms": ms}
             c = captures.get((name, frames_per_launch))
-            if c:
+            it_cap = c.get("iterations_mean_at_capture") if c else None
+            if c and it_cap and iters and abs(iters / it_cap - 1.0) > 0.02:
+                # the per-launch instruction / flop counts belong to another iteration count (solver parameters changed since the
+                # capture, e.g. the initial damping): DRAM traffic is input-bound and stays valid, the two derived fractions do not
+                r["traffic"] = c.get("dram_bytes_per_launch")
+                r["note"] = (f"issue / fp32 withheld: captured at {it_cap:.3f} iterations per frame, this run solves at {iters:.3f} "
+                             "(same library build, other solver parameters); profiles/r02/prof_*.md hold the capture")
+            elif c:
                 r["traffic"] = c.get("dram_bytes_per_launch")
                 if c.get("warp_inst_per_launch"):
                     a = c["warp_inst_per_launch"] / (ms * 1e-3)
@@ -590,7 +597,7 @@ def main():
 
         mean_launch_ms = statistics.mean(launch_ms)
         value = B * world * args.steps / (total_ms * 1e-3)
-        rl = roof("metric", B, mean_launch_ms, bytes_per_frame(opt))
+        rl = roof("metric", B, mean_launch_ms, bytes_per_frame(opt), iters_mean)
         rl.update(launch_ms_mean=mean_launch_ms, launch_ms_min=min(launch_ms), launch_ms_max=max(launch_ms),
                   note="latency / FP32-issue bound solver: `issue` and `fp32` are the rooflines that bind (DESIGN.md 3.4)")
         for rec in records:
@@ -603,7 +610,7 @@ def main():
             rec["n_gpus"] = world
             if rec["name"] == "leap_dexpilot_streams":
                 rec["us_per_frame_per_stream"] = ms * 1e3 / rec["steps"]
-            rec["roofline"] = roof(rec["name"], per_gpu, ms, rec["bytes_per_frame"])
+            rec["roofline"] = roof(rec["name"], per_gpu, ms, rec["bytes_per_frame"], rec.get("iterations_mean"))
         line = {
             "metric": "hand_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -19,6 +19,16 @@ for name in ("launches_bench.csv", "clocks.csv"):
 shutil.copy(src / "roofline_traffic.json", ROOT / "profiles" / "roofline_traffic.json")
 line = json.loads((src / "bench.json").read_text().strip().splitlines()[-1])
 (dst / "bench_1gpu.json").write_text(json.dumps(line, indent=1) + "\n")
+# the captures belong to the iteration counts of this run: bench.py withholds the derived issue / fp32 fractions when a later run
+# of the same library solves at other counts (solver parameters changed)
+tpath = ROOT / "profiles" / "roofline_traffic.json"
+tj = json.loads(tpath.read_text())
+iters = {"metric": line["solver"]["mean_iterations"], **{c["name"]: c["iterations_mean"] for c in line["configs"] if c.get("iterations_mean") is not None}}
+for key, cap in tj["captures"].items():
+    name = key.split("@")[0]
+    if name in iters and (("@" not in key) or cap.get("frames_per_launch") == next((c.get("streams_per_gpu", 0) * c.get("steps", 0) for c in line["configs"] if c["name"] == name), None)):
+        cap["iterations_mean_at_capture"] = round(float(iters[name]), 4)
+tpath.write_text(json.dumps(tj, indent=1) + "\n")
 ref = json.loads((src / "bench_reference.json").read_text().strip().splitlines()[-1])
 (dst / "bench_reference_arm.json").write_text(json.dumps(ref, indent=1) + "\n")
 par = {"build_id": line["solver"]["build_id"], "tolerance_rad": 1e-4,
