@@ -217,6 +217,52 @@ KIND_NOTE = {"port": "restated reference path (C FK/Jacobian + numpy loss + scip
 
 
 # --------------------------------------------------------------------------------------- main
+def load_captures(build_id, path=None):
+    """profiles/roofline_traffic.json -> {(bench record name, frames per launch): capture} for the captures taken from THIS library
+    build, plus a note when the file belongs to another build (then nothing derived from it is reported)."""
+    captures, cap_note = {}, None
+    tpath = Path(path) if path else ROOT / "profiles" / "roofline_traffic.json"
+    if tpath.exists():
+        tj = json.loads(tpath.read_text())
+        tj = tj if "captures" in tj else {"captures": {"metric": tj}}
+        for name, c in tj["captures"].items():
+            if c.get("build_id") == build_id:
+                captures[(name.split("@")[0], c.get("frames_per_launch"))] = c
+        if not captures:
+            cap_note = f"profiles/roofline_traffic.json was captured from another library build (loaded build {build_id}): traffic / issue / fp32 withheld"
+    return captures, cap_note
+
+
+def roofline_record(c, cap_note, frames_per_launch, ms, bpf, iters, peak, peak_src, peak_issue, peak_fp32):
+    """One `roofline` object: the contract figure (algorithmic HBM bytes / launch time vs the measured copy peak) and, from the
+    ncu capture `c` of the same build, DRAM traffic and the two fractions that actually bind (issue slots, FP32)."""
+    ach = bpf * frames_per_launch / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+         "peak_source": peak_src, "bytes_per_frame": bpf, "launch_ms": ms}
+    it_cap = c.get("iterations_mean_at_capture") if c else None
+    if c and it_cap and iters and abs(iters / it_cap - 1.0) > 0.02:
+        # the per-launch instruction / flop counts belong to another iteration count (solver parameters changed since the
+        # capture, e.g. the initial damping): DRAM traffic is input-bound and stays valid, the two derived fractions do not
+        r["traffic"] = c.get("dram_bytes_per_launch")
+        r["note"] = (f"issue / fp32 withheld: captured at {it_cap:.3f} iterations per frame, this run solves at {iters:.3f} "
+                     "(same library build, other solver parameters); profiles/r02/prof_*.md hold the capture")
+    elif c:
+        r["traffic"] = c.get("dram_bytes_per_launch")
+        if c.get("warp_inst_per_launch"):
+            a = c["warp_inst_per_launch"] / (ms * 1e-3)
+            r["issue"] = {"achieved": a, "peak": peak_issue, "unit": "warp-inst/s", "frac": a / peak_issue,
+                          "warp_inst_per_frame": c["warp_inst_per_launch"] / frames_per_launch}
+        if c.get("fp32_flop_per_launch"):
+            a = c["fp32_flop_per_launch"] / (ms * 1e-3)
+            r["fp32"] = {"flops_per_frame": c["fp32_flop_per_launch"] / frames_per_launch, "achieved": a / 1e12, "peak": peak_fp32 / 1e12,
+                         "unit": "TFLOP/s", "frac": a / peak_fp32,
+                         "counted": "executed FFMA x 2 + FADD + FMUL thread instructions (ncu smsp__sass_thread_inst_executed_op_*), same capture"}
+        r["capture"] = {"build_id": c.get("build_id"), "source": c.get("source")}
+    elif cap_note:
+        r["note"] = cap_note
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -556,44 +602,11 @@ def main():
         peak_issue = 4 * props.multi_processor_count * sm_mhz * 1e6
         peak_fp32 = 2 * FP32_LANES_PER_SM * props.multi_processor_count * sm_mhz * 1e6
         build_id = NATIVE.build_id()
-        captures, cap_note = {}, None
-        tpath = ROOT / "profiles" / "roofline_traffic.json"
-        if tpath.exists():
-            tj = json.loads(tpath.read_text())
-            tj = tj if "captures" in tj else {"captures": {"metric": tj}}
-            for name, c in tj["captures"].items():
-                if c.get("build_id") == build_id:
-                    captures[(name.split("@")[0], c.get("frames_per_launch"))] = c
-            if not captures:
-                cap_note = f"profiles/roofline_traffic.json was captured from another library build (loaded build {build_id}): traffic / issue / fp32 withheld"
+        captures, cap_note = load_captures(build_id)
 
         def roof(name, frames_per_launch, ms, bpf, iters=None):
-            ach = bpf * frames_per_launch / (ms * 1e-3) / 1e9
-            r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                 "peak_source": peak_src, "bytes_per_frame": bpf, "launch_ms": ms}
-            c = captures.get((name, frames_per_launch))
-            it_cap = c.get("iterations_mean_at_capture") if c else None
-            if c and it_cap and iters and abs(iters / it_cap - 1.0) > 0.02:
-                # the per-launch instruction / flop counts belong to another iteration count (solver parameters changed since the
-                # capture, e.g. the initial damping): DRAM traffic is input-bound and stays valid, the two derived fractions do not
-                r["traffic"] = c.get("dram_bytes_per_launch")
-                r["note"] = (f"issue / fp32 withheld: captured at {it_cap:.3f} iterations per frame, this run solves at {iters:.3f} "
-                             "(same library build, other solver parameters); profiles/r02/prof_*.md hold the capture")
-            elif c:
-                r["traffic"] = c.get("dram_bytes_per_launch")
-                if c.get("warp_inst_per_launch"):
-                    a = c["warp_inst_per_launch"] / (ms * 1e-3)
-                    r["issue"] = {"achieved": a, "peak": peak_issue, "unit": "warp-inst/s", "frac": a / peak_issue,
-                                  "warp_inst_per_frame": c["warp_inst_per_launch"] / frames_per_launch}
-                if c.get("fp32_flop_per_launch"):
-                    a = c["fp32_flop_per_launch"] / (ms * 1e-3)
-                    r["fp32"] = {"flops_per_frame": c["fp32_flop_per_launch"] / frames_per_launch, "achieved": a / 1e12, "peak": peak_fp32 / 1e12,
-                                 "unit": "TFLOP/s", "frac": a / peak_fp32,
-                                 "counted": "executed FFMA x 2 + FADD + FMUL thread instructions (ncu smsp__sass_thread_inst_executed_op_*), same capture"}
-                r["capture"] = {"build_id": c.get("build_id"), "source": c.get("source")}
-            elif cap_note:
-                r["note"] = cap_note
-            return r
+            return roofline_record(captures.get((name, frames_per_launch)), cap_note, frames_per_launch, ms, bpf, iters,
+                                   peak, peak_src, peak_issue, peak_fp32)
 
         mean_launch_ms = statistics.mean(launch_ms)
         value = B * world * args.steps / (total_ms * 1e-3)
