@@ -51,9 +51,12 @@ def test_arrow_matches_dense_and_oracle_warm(key):
         d = gpu_solve(opt, refs, fixed, x0)
     assert int((a["status"] >> 24).max()) == 0 and int((d["status"] >> 24).max()) == 0
     # same Newton systems, different elimination order: the iterates agree to rounding, the minimiser to the fp32 resolution
-    # of the configuration (free-flying bases put the links metres from the origin: ulp(p) / lever arm ~ 1e-5 ... 4e-5 rad;
-    # measured on B200: 2.4e-5 on offline/allegro_hand_right, below 1e-5 elsewhere); both are held to the oracle below
-    assert np.abs(a["q"] - d["q"]).max() < 5e-5
+    # of the configuration (free-flying bases put the links metres from the origin: ulp(p) / lever arm ~ 1e-5 ... 4e-5 rad).
+    # Which hand shows the largest difference moves with every change of the damping schedule -- measured on B200: 2.4e-5 on
+    # offline/allegro_hand_right; emulated: 4.2e-5 on offline/leap_hand_left at lambda0 = 1e-2, 1.9e-5 on
+    # offline/shadow_hand_right at 1e-3, 5e-7 ... 6e-6 elsewhere -- so the two factorisations are held to each other at the
+    # parity tolerance, and both to the oracle below
+    assert np.abs(a["q"] - d["q"]).max() < TOL
     np.testing.assert_allclose(a["cost"], d["cost"], rtol=2e-4, atol=1e-8)  # fp32 sums in a different order
     assert abs(float((a["status"] & 0xffff).mean()) - float((d["status"] & 0xffff).mean())) < 0.5
     XB, _ = oracle_b(o, refs, fixed, x0)
