@@ -35,6 +35,36 @@ class StreamState:
     projected: Optional["torch.Tensor"]  # [S, len_proj] uint8 (DexPilot) or None
     damping: Optional["torch.Tensor"] = None  # [S] float32: the solver's carried damping (dexr_sequences_t.damping_state)
 
+    _FIELDS = ("last_qpos", "filter_state", "filter_init", "projected", "damping")
+
+    def state_dict(self) -> dict:
+        """Host copies of every tensor (None stays None): what a checkpoint of S running streams has to hold.  A run resumed
+        from it continues bit-identically (the state is complete: tests/test_gpu_parity.py splits a call in two)."""
+        return {k: (None if getattr(self, k) is None else getattr(self, k).detach().cpu().clone()) for k in self._FIELDS}
+
+    @classmethod
+    def from_state_dict(cls, state: dict, device=None) -> "StreamState":
+        """Inverse of `state_dict` (tensors moved to `device`); a checkpoint written before `damping` existed resumes with the
+        solver's default damping."""
+        import torch
+
+        missing = [k for k in cls._FIELDS[:3] if state.get(k) is None]
+        if missing:
+            raise ValueError(f"stream state checkpoint lacks {missing}")
+        S = int(state["last_qpos"].shape[0])
+        for k in cls._FIELDS[1:]:
+            t = state.get(k)
+            if t is not None and int(t.shape[0]) != S:
+                raise ValueError(f"stream state checkpoint: {k} holds {int(t.shape[0])} streams, last_qpos {S}")
+
+        def put(t):
+            return None if t is None else torch.as_tensor(t).to(device if device is not None else t.device).contiguous()
+
+        st = cls(**{k: put(state.get(k)) for k in cls._FIELDS})
+        if st.damping is None:
+            st.damping = torch.zeros((S,), dtype=torch.float32, device=st.last_qpos.device)
+        return st
+
 
 def _quat_to_matrix(q):
     w, x, y, z = (float(v) for v in q)

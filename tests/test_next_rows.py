@@ -53,3 +53,30 @@ def test_trajectory_pickle_roundtrip(tmp_path):
     assert meta["dof"] == 16 and meta["joint_names"] == seq.joint_names and meta["config_path"].endswith("leap_hand_right.yml")
     with pytest.raises(ValueError):
         save_trajectory(tmp_path / "bad.pkl", q[:, :3], seq.joint_names)
+
+
+def test_stream_state_checkpoint_round_trip():
+    """StreamState.state_dict / from_state_dict: host copies of every tensor, None kept, shapes checked, and a checkpoint from
+    before the carried damping existed resumes at the solver's default (zeros)."""
+    import torch
+
+    from dex_retargeting_b200.seq_retarget import StreamState
+
+    S = 5
+    st = StreamState(last_qpos=torch.randn(S, 16), filter_state=torch.randn(S, 16), filter_init=torch.ones(S, dtype=torch.uint8),
+                     projected=torch.zeros(S, 6, dtype=torch.uint8), damping=torch.full((S,), 0.3))
+    sd = st.state_dict()
+    assert set(sd) == {"last_qpos", "filter_state", "filter_init", "projected", "damping"}
+    sd["last_qpos"][0, 0] = 99.0  # a copy, not a view
+    assert float(st.last_qpos[0, 0]) != 99.0
+    back = StreamState.from_state_dict(st.state_dict())
+    for k in sd:
+        assert torch.equal(getattr(back, k), getattr(st, k)) and getattr(back, k).is_contiguous()
+    old = {k: v for k, v in st.state_dict().items() if k != "damping"}
+    old["projected"] = None
+    back = StreamState.from_state_dict(old)
+    assert back.projected is None and torch.equal(back.damping, torch.zeros(S))
+    with pytest.raises(ValueError, match="lacks"):
+        StreamState.from_state_dict({"last_qpos": st.last_qpos})
+    with pytest.raises(ValueError, match="streams"):
+        StreamState.from_state_dict({**st.state_dict(), "filter_init": torch.ones(S + 1, dtype=torch.uint8)})
